@@ -1,0 +1,131 @@
+"""ctypes binding of libglom_b200.so (include/glom_b200.h).  No torch types cross the ABI:
+only raw device pointers, sizes and the stream handle.  There is no fallback: if the library
+is missing or fails to load, importing the engine raises."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libglom_b200.so")
+
+ABI_VERSION = 1
+PRECISION = {"fp32": 0, "bf16": 1}
+
+EXPORTS = (
+    "glom_b200_abi_version", "glom_b200_last_error", "glom_b200_packed_weight_bytes",
+    "glom_b200_pack_weights", "glom_b200_workspace_bytes", "glom_b200_forward",
+    "glom_b200_tokenize", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
+    "glom_b200_profile_begin", "glom_b200_profile_end",
+)
+PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize")
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("dim", ctypes.c_int32), ("levels", ctypes.c_int32),
+                ("n", ctypes.c_int32), ("attend_self", ctypes.c_int32), ("mask_side", ctypes.c_int32),
+                ("mask_d2_max", ctypes.c_int32), ("precision", ctypes.c_int32)]
+
+
+class WeightsRef(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [
+        (k, ctypes.c_void_p) for k in ("bu_w1", "bu_b1", "bu_w2", "bu_b2", "td_w1", "td_b1", "td_w2", "td_b2")]
+
+
+class GlomB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GlomB200Error(
+            f"{LIB_PATH} not found: build it with `python -m glom_pytorch_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the GLOM column update.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.glom_b200_abi_version.restype = i32
+    lib.glom_b200_last_error.restype = ctypes.c_char_p
+    lib.glom_b200_last_launch_count.restype = i32
+    lib.glom_b200_packed_weight_bytes.argtypes = [ctypes.POINTER(Cfg), ctypes.POINTER(sz)]
+    lib.glom_b200_pack_weights.argtypes = [ctypes.POINTER(Cfg), ctypes.POINTER(WeightsRef), vp, sz, vp]
+    lib.glom_b200_workspace_bytes.argtypes = [ctypes.POINTER(Cfg), i32, i32, i32, ctypes.POINTER(sz)]
+    lib.glom_b200_workspace_offset.argtypes = [ctypes.POINTER(Cfg), i32, i32, i32, i32,
+                                               ctypes.POINTER(sz), ctypes.POINTER(sz)]
+    lib.glom_b200_forward.argtypes = [ctypes.POINTER(Cfg), vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.glom_b200_tokenize.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.glom_b200_profile_begin.restype = i32
+    lib.glom_b200_profile_end.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
+    lib.glom_b200_profile_end.restype = i32
+    for f in ("glom_b200_packed_weight_bytes", "glom_b200_pack_weights", "glom_b200_workspace_bytes",
+              "glom_b200_workspace_offset", "glom_b200_forward", "glom_b200_tokenize"):
+        getattr(lib, f).restype = i32
+    if lib.glom_b200_abi_version() != ABI_VERSION:
+        raise GlomB200Error(f"libglom_b200 ABI {lib.glom_b200_abi_version()} != expected {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GlomB200Error(f"glom_b200 error {rc}: {load().glom_b200_last_error().decode()}")
+
+
+def make_cfg(dim, levels, n, attend_self, mask_side, mask_d2_max, precision):
+    return Cfg(ctypes.sizeof(Cfg), dim, levels, n, int(bool(attend_self)), mask_side, mask_d2_max,
+               PRECISION[precision])
+
+
+def packed_weight_bytes(cfg):
+    out = ctypes.c_size_t()
+    check(load().glom_b200_packed_weight_bytes(ctypes.byref(cfg), ctypes.byref(out)))
+    return out.value
+
+
+def workspace_bytes(cfg, batch, iters, return_all):
+    out = ctypes.c_size_t()
+    check(load().glom_b200_workspace_bytes(ctypes.byref(cfg), batch, iters, int(return_all), ctypes.byref(out)))
+    return out.value
+
+
+def workspace_offset(cfg, batch, iters, return_all, which):
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    check(load().glom_b200_workspace_offset(ctypes.byref(cfg), batch, iters, int(return_all), which,
+                                            ctypes.byref(off), ctypes.byref(nb)))
+    return off.value, nb.value
+
+
+def pack_weights(cfg, ptrs, packed_ptr, packed_bytes, stream):
+    w = WeightsRef(ctypes.sizeof(WeightsRef), *ptrs)
+    check(load().glom_b200_pack_weights(ctypes.byref(cfg), ctypes.byref(w), packed_ptr, packed_bytes, stream))
+
+
+def forward(cfg, packed_ptr, tokens_ptr, pos_ptr, state_in_ptr, init_ptr, out_ptr, batch, iters,
+            return_all, ws_ptr, ws_bytes, stream):
+    check(load().glom_b200_forward(ctypes.byref(cfg), packed_ptr, tokens_ptr, pos_ptr, state_in_ptr, init_ptr,
+                                   out_ptr, batch, iters, int(return_all), ws_ptr, ws_bytes, stream))
+
+
+def tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim, stream):
+    check(load().glom_b200_tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim, stream))
+
+
+def last_launch_count():
+    return load().glom_b200_last_launch_count()
+
+
+def profile_begin():
+    check(load().glom_b200_profile_begin())
+
+
+def profile_end():
+    """-> {kind: (milliseconds, launches)} for the kernels enqueued since profile_begin()."""
+    k = len(PROFILE_KINDS)
+    ms = (ctypes.c_double * k)()
+    cnt = (ctypes.c_int * k)()
+    check(load().glom_b200_profile_end(ms, cnt, k))
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(PROFILE_KINDS)}

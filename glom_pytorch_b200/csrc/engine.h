@@ -1,0 +1,114 @@
+// Internal engine declarations shared by the C-ABI translation unit and the kernel files.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <vector>
+
+namespace glom {
+
+// Optional per-kernel CUDA-event timing (bench.py's roofline numbers).  Events are recorded on the
+// launch stream around each kernel; nothing is synchronised until the caller reads them.
+enum ProfKind { PROF_ATTN = 0, PROF_GEMM1 = 1, PROF_GEMM2 = 2, PROF_PREP = 3, PROF_TOKENIZE = 4, PROF_KINDS = 5 };
+struct Profiler {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  struct Span { int kind; size_t a, b; };
+  std::vector<Span> spans;
+  size_t mark(cudaStream_t st) {
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[used], st);
+    return used++;
+  }
+};
+struct ProfScope {   // RAII: events around one launch when profiling is on
+  Profiler* p; int kind; cudaStream_t st; size_t a;
+  ProfScope(Profiler* p_, int kind_, cudaStream_t st_) : p(p_ && p_->enabled ? p_ : nullptr), kind(kind_), st(st_), a(0) {
+    if (p) a = p->mark(st);
+  }
+  ~ProfScope() { if (p) { const size_t b = p->mark(st); p->spans.push_back({kind, a, b}); } }
+};
+
+struct Geometry {
+  int d, L, n, B;
+  int rows;        // B * n   (columns of the batch = GEMM M)
+  int G;           // 2L - 1  MLP groups, ordered bu_0, td_0, bu_1, td_1, ..., bu_{L-1}
+  int hidden;      // 4d
+  int attend_self, mask_side, mask_d2_max;
+  int bn2;         // N tile of the second GEMM: 256 / 128 / 64 (largest dividing d)
+  int nparts;      // squared-norm partials per (row, level) = 2 * d / bn2
+};
+
+// ---- packed weights -------------------------------------------------------------------------
+// bf16 engine:  W1p [(G*4d) x d] bf16 | W2p [(L*d) x 8d] bf16 | b1p [G*4d] f32 | b2p [L*d] f32
+// fp32 engine:  same shapes, all f32.
+struct PackedLayout {
+  size_t w1_off, w2_off, b1_off, b2_off, total;
+};
+PackedLayout packed_layout(int d, int L, int precision);
+
+// ---- workspace ------------------------------------------------------------------------------
+struct WorkspaceLayout {
+  size_t s32_off;      // one fp32 state slab (ping-pong partner of state_out); 0 bytes if return_all
+  size_t s32_bytes;
+  size_t sb_off[2];    // bf16 shadow of the state           (rows, L, d)
+  size_t sp_off[2];    // bf16 shadow of state[:, :, 1:] + pos (rows, L-1, d)
+  size_t xb_off;       // bf16 tokens                        (rows, d)
+  size_t h_off;        // hidden activations                 (rows, G*4d)   bf16 | f32
+  size_t h_bytes;
+  size_t c_off;        // consensus output                   (rows, L, d)   bf16 | f32
+  size_t c_bytes;
+  size_t nsq_off[2];   // squared-norm partials              (rows, L, nparts) f32
+  size_t nsq_bytes;
+  size_t total;
+};
+WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, int return_all);
+
+// ---- launchers (return cudaError_t of the launch; all asynchronous on `st`) -----------------
+struct Bf16Buffers {
+  const float* s32_in;  float* s32_out;              // fp32 master state of step t / t+1
+  const __nv_bfloat16* sb_in;  __nv_bfloat16* sb_out;
+  const __nv_bfloat16* sp_in;  __nv_bfloat16* sp_out;
+  const __nv_bfloat16* xb;
+  __nv_bfloat16* h;  __nv_bfloat16* c;
+  const float* nsq_in;  float* nsq_out;
+  const float* pos;                                   // (n, d) fp32
+  const __nv_bfloat16* w1;  const __nv_bfloat16* w2;  const float* b1;  const float* b2;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// state prologue: S_0 -> fp32 master copy (dst may equal src => skipped), bf16 shadows, norms, bf16 tokens
+cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* init_levels, const float* pos,
+                        const float* tokens, float* s32_dst, __nv_bfloat16* sb, __nv_bfloat16* sp,
+                        __nv_bfloat16* xb, float* nsq, cudaStream_t st, int* launches, Profiler* prof);
+
+// one Jacobi step on tensor cores: consensus -> C ; GEMM1+GELU -> H ; GEMM2+combine -> state t+1
+int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st,
+              int* launches, char* err, size_t errlen, Profiler* prof);
+
+struct F32Buffers {
+  const float* s_in;  float* s_out;
+  const float* x;  const float* pos;
+  float* h;  float* c;
+  const float* w1;  const float* w2;  const float* b1;  const float* b2;
+};
+cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, int* launches, Profiler* prof);
+cudaError_t launch_broadcast_init(const Geometry& g, const float* state_in, const float* init_levels, float* dst,
+                                  cudaStream_t st, int* launches, Profiler* prof);
+
+cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const float* bu_b1, const float* bu_w2,
+                        const float* bu_b2, const float* td_w1, const float* td_b1, const float* td_w2,
+                        const float* td_b2, void* packed, cudaStream_t st, int* launches);
+
+cudaError_t launch_tokenize(const float* img, const float* w, const float* bias, float* tokens, int B, int H, int W,
+                            int p, int d, cudaStream_t st, int* launches, Profiler* prof);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace glom

@@ -1,0 +1,299 @@
+// C ABI of libglom_b200.so (see include/glom_b200.h).  Host logic only: argument checking,
+// buffer layout, the per-step launch sequence.  No device allocation, no stream sync.
+#include "../../include/glom_b200.h"
+#include "engine.h"
+
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace glom {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+static thread_local Profiler g_prof;
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+PackedLayout packed_layout(int d, int L, int precision) {
+  const size_t es = precision == GLOM_B200_BF16 ? 2 : 4;
+  const size_t G = 2 * (size_t)L - 1;
+  PackedLayout p;
+  size_t off = 0;
+  p.w1_off = off; off = align_up(off + G * 4 * d * d * es, 1024);
+  p.w2_off = off; off = align_up(off + (size_t)L * d * 8 * d * es, 1024);
+  p.b1_off = off; off = align_up(off + G * 4 * d * 4, 1024);
+  p.b2_off = off; off = align_up(off + (size_t)L * d * 4, 1024);
+  p.total = off;
+  return p;
+}
+
+WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, int return_all) {
+  WorkspaceLayout w{};
+  const size_t state_elems = (size_t)g.rows * g.L * g.d;
+  size_t off = 0;
+  w.s32_off = off;
+  w.s32_bytes = (return_all || iters == 0) ? 0 : state_elems * 4;
+  off = align_up(off + w.s32_bytes, 1024);
+  if (precision == GLOM_B200_BF16) {
+    for (int i = 0; i < 2; ++i) { w.sb_off[i] = off; off = align_up(off + state_elems * 2, 1024); }
+    for (int i = 0; i < 2; ++i) { w.sp_off[i] = off; off = align_up(off + (size_t)g.rows * (g.L - 1) * g.d * 2, 1024); }
+    w.xb_off = off; off = align_up(off + (size_t)g.rows * g.d * 2, 1024);
+    w.h_bytes = (size_t)g.rows * g.G * 4 * g.d * 2;
+    w.c_bytes = state_elems * 2;
+    w.nsq_bytes = (size_t)g.rows * g.L * g.nparts * 4;
+  } else {
+    w.h_bytes = (size_t)g.rows * g.G * 4 * g.d * 4;
+    w.c_bytes = state_elems * 4;
+    w.nsq_bytes = 0;
+  }
+  w.h_off = off; off = align_up(off + w.h_bytes, 1024);
+  w.c_off = off; off = align_up(off + w.c_bytes, 1024);
+  for (int i = 0; i < 2; ++i) { w.nsq_off[i] = off; off = align_up(off + w.nsq_bytes, 1024); }
+  w.total = off > 0 ? off : 1024;
+  return w;
+}
+
+static int check_cfg(const glom_b200_cfg* cfg) {
+  if (!cfg) return fail(GLOM_B200_ERR_INVALID, "cfg is NULL");
+  if (cfg->struct_size != sizeof(glom_b200_cfg))
+    return fail(GLOM_B200_ERR_INVALID, "cfg.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(glom_b200_cfg));
+  if (cfg->levels < 2) return fail(GLOM_B200_ERR_INVALID, "levels must be >= 2 (got %d)", cfg->levels);
+  if (cfg->dim < 4 || cfg->dim % 4) return fail(GLOM_B200_ERR_INVALID, "dim must be a positive multiple of 4 (got %d)", cfg->dim);
+  if (cfg->n < 1) return fail(GLOM_B200_ERR_INVALID, "n must be >= 1 (got %d)", cfg->n);
+  if (cfg->precision != GLOM_B200_FP32 && cfg->precision != GLOM_B200_BF16)
+    return fail(GLOM_B200_ERR_INVALID, "unknown precision %d", cfg->precision);
+  if (cfg->precision == GLOM_B200_BF16 && cfg->dim % 64)
+    return fail(GLOM_B200_ERR_INVALID, "bf16 (tcgen05) precision needs dim %% 64 == 0 (got %d); use fp32 precision", cfg->dim);
+  if (cfg->mask_side < 0 || (cfg->mask_side > 0 && cfg->n % cfg->mask_side))
+    return fail(GLOM_B200_ERR_INVALID, "mask_side %d does not tile n = %d", cfg->mask_side, cfg->n);
+  return 0;
+}
+
+static Geometry make_geometry(const glom_b200_cfg* cfg, int batch) {
+  Geometry g{};
+  g.d = cfg->dim; g.L = cfg->levels; g.n = cfg->n; g.B = batch;
+  g.rows = batch * cfg->n;
+  g.G = 2 * g.L - 1;
+  g.hidden = 4 * g.d;
+  g.attend_self = cfg->attend_self; g.mask_side = cfg->mask_side; g.mask_d2_max = cfg->mask_d2_max;
+  g.bn2 = (g.d % 256 == 0) ? 256 : (g.d % 128 == 0) ? 128 : 64;
+  g.nparts = 2 * g.d / g.bn2;
+  return g;
+}
+
+struct DeviceInfo { bool ok; int sms; };
+static std::mutex g_mu;
+static DeviceInfo g_dev[64];
+static bool g_dev_known[64];
+static EncodeTiledFn g_encode = nullptr;
+
+static int device_info(DeviceInfo* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return fail(GLOM_B200_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_dev_known[dev]) {
+    int major = 0, sms = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    g_dev[dev].ok = (major == 10);
+    g_dev[dev].sms = sms;
+    g_dev_known[dev] = true;
+  }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn)
+      return fail(GLOM_B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = g_dev[dev];
+  if (!out->ok) return fail(GLOM_B200_ERR_DEVICE, "device %d is not compute capability 10.x (sm_100a kernels only)", dev);
+  return 0;
+}
+
+}  // namespace glom
+
+using namespace glom;
+
+extern "C" {
+
+GLOM_B200_API int glom_b200_abi_version(void) { return GLOM_B200_ABI_VERSION; }
+
+GLOM_B200_API const char* glom_b200_last_error(void) { return g_err; }
+
+GLOM_B200_API int glom_b200_last_launch_count(void) { return g_launches; }
+
+GLOM_B200_API int glom_b200_packed_weight_bytes(const glom_b200_cfg* cfg, size_t* out_bytes) {
+  if (int r = check_cfg(cfg)) return r;
+  if (!out_bytes) return fail(GLOM_B200_ERR_INVALID, "out_bytes is NULL");
+  *out_bytes = packed_layout(cfg->dim, cfg->levels, cfg->precision).total;
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_pack_weights(const glom_b200_cfg* cfg, const glom_b200_weights_ref* w, void* packed, size_t packed_bytes,
+                           void* stream) {
+  if (int r = check_cfg(cfg)) return r;
+  if (!w || w->struct_size != sizeof(glom_b200_weights_ref)) return fail(GLOM_B200_ERR_INVALID, "weights struct missing or wrong size");
+  if (!w->bu_w1 || !w->bu_b1 || !w->bu_w2 || !w->bu_b2 || !w->td_w1 || !w->td_b1 || !w->td_w2 || !w->td_b2)
+    return fail(GLOM_B200_ERR_INVALID, "a weight pointer is NULL");
+  const PackedLayout pl = packed_layout(cfg->dim, cfg->levels, cfg->precision);
+  if (!packed || packed_bytes < pl.total) return fail(GLOM_B200_ERR_WORKSPACE, "packed buffer: need %zu bytes, got %zu", pl.total, packed_bytes);
+  if (reinterpret_cast<uintptr_t>(packed) % 1024) return fail(GLOM_B200_ERR_INVALID, "packed buffer must be 1024-byte aligned");
+  g_launches = 0;
+  cudaError_t e = launch_pack(cfg->dim, cfg->levels, cfg->precision, w->bu_w1, w->bu_b1, w->bu_w2, w->bu_b2, w->td_w1,
+                              w->td_b1, w->td_w2, w->td_b2, packed, static_cast<cudaStream_t>(stream), &g_launches);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_workspace_bytes(const glom_b200_cfg* cfg, int batch, int iters, int return_all, size_t* out_bytes) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || iters < 0 || !out_bytes) return fail(GLOM_B200_ERR_INVALID, "bad batch/iters/out_bytes");
+  *out_bytes = workspace_layout(make_geometry(cfg, batch), cfg->precision, iters, return_all).total;
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch, int iters, int return_all, int which,
+                               size_t* out_offset, size_t* out_bytes) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || iters < 0 || !out_offset || !out_bytes) return fail(GLOM_B200_ERR_INVALID, "bad arguments");
+  const WorkspaceLayout w = workspace_layout(make_geometry(cfg, batch), cfg->precision, iters, return_all);
+  switch (which) {
+    case 0: *out_offset = w.h_off; *out_bytes = w.h_bytes; return 0;
+    case 1: *out_offset = w.c_off; *out_bytes = w.c_bytes; return 0;
+    case 2: *out_offset = w.nsq_off[0]; *out_bytes = w.nsq_bytes; return 0;
+    default: return fail(GLOM_B200_ERR_INVALID, "unknown workspace buffer id %d", which);
+  }
+}
+
+GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens, const float* pos,
+                      const float* state_in, const float* init_levels, float* state_out, int batch, int iters,
+                      int return_all, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || iters < 0) return fail(GLOM_B200_ERR_INVALID, "batch must be >= 1 and iters >= 0");
+  if (!packed_weights || !tokens || !pos || !state_out) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
+  if (!state_in && !init_levels) return fail(GLOM_B200_ERR_INVALID, "need state_in or init_levels");
+  if (state_in == state_out) return fail(GLOM_B200_ERR_INVALID, "state_out must not alias state_in");
+  if (reinterpret_cast<uintptr_t>(packed_weights) % 1024 || reinterpret_cast<uintptr_t>(workspace) % 1024)
+    return fail(GLOM_B200_ERR_INVALID, "packed weights and workspace must be 1024-byte aligned");
+  if (reinterpret_cast<uintptr_t>(tokens) % 16 || reinterpret_cast<uintptr_t>(pos) % 16 ||
+      reinterpret_cast<uintptr_t>(state_out) % 16 || reinterpret_cast<uintptr_t>(state_in) % 16 ||
+      reinterpret_cast<uintptr_t>(init_levels) % 16)
+    return fail(GLOM_B200_ERR_INVALID, "tensor pointers must be 16-byte aligned");
+  DeviceInfo di{};
+  if (int r = device_info(&di)) return r;
+  const Geometry g = make_geometry(cfg, batch);
+  const WorkspaceLayout wl = workspace_layout(g, cfg->precision, iters, return_all);
+  if (!workspace || workspace_bytes < wl.total)
+    return fail(GLOM_B200_ERR_WORKSPACE, "workspace: need %zu bytes, got %zu", wl.total, workspace_bytes);
+  const PackedLayout pl = packed_layout(g.d, g.L, cfg->precision);
+  const char* pw = static_cast<const char*>(packed_weights);
+  char* ws = static_cast<char*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t slab = (size_t)g.rows * g.L * g.d;
+  g_launches = 0;
+
+  // where the fp32 master of step t lives
+  float* wslab = reinterpret_cast<float*>(ws + wl.s32_off);
+  auto loc = [&](int t) -> float* {
+    if (return_all) return state_out + (size_t)t * slab;
+    return ((iters - t) % 2 == 0) ? state_out : wslab;
+  };
+
+  if (cfg->precision == GLOM_B200_BF16) {
+    __nv_bfloat16* sb[2] = {reinterpret_cast<__nv_bfloat16*>(ws + wl.sb_off[0]), reinterpret_cast<__nv_bfloat16*>(ws + wl.sb_off[1])};
+    __nv_bfloat16* sp[2] = {reinterpret_cast<__nv_bfloat16*>(ws + wl.sp_off[0]), reinterpret_cast<__nv_bfloat16*>(ws + wl.sp_off[1])};
+    float* nsq[2] = {reinterpret_cast<float*>(ws + wl.nsq_off[0]), reinterpret_cast<float*>(ws + wl.nsq_off[1])};
+    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
+    cudaError_t e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
+    if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "prep launch: %s", cudaGetErrorString(e));
+    for (int t = 0; t < iters; ++t) {
+      Bf16Buffers b{};
+      b.s32_in = loc(t); b.s32_out = loc(t + 1);
+      b.sb_in = sb[t & 1]; b.sb_out = sb[(t + 1) & 1];
+      b.sp_in = sp[t & 1]; b.sp_out = sp[(t + 1) & 1];
+      b.xb = xb;
+      b.h = reinterpret_cast<__nv_bfloat16*>(ws + wl.h_off);
+      b.c = reinterpret_cast<__nv_bfloat16*>(ws + wl.c_off);
+      b.nsq_in = nsq[t & 1]; b.nsq_out = nsq[(t + 1) & 1];
+      b.pos = pos;
+      b.w1 = reinterpret_cast<const __nv_bfloat16*>(pw + pl.w1_off);
+      b.w2 = reinterpret_cast<const __nv_bfloat16*>(pw + pl.w2_off);
+      b.b1 = reinterpret_cast<const float*>(pw + pl.b1_off);
+      b.b2 = reinterpret_cast<const float*>(pw + pl.b2_off);
+      char msg[400] = "";
+      const int r = step_bf16(g, b, g_encode, di.sms, st, &g_launches, msg, sizeof(msg), &g_prof);
+      if (r) return fail(r == -1 ? GLOM_B200_ERR_INVALID : GLOM_B200_ERR_CUDA, "step %d: %s", t, msg);
+    }
+  } else {
+    cudaError_t e = launch_broadcast_init(g, state_in, init_levels, loc(0), st, &g_launches, &g_prof);
+    if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "init launch: %s", cudaGetErrorString(e));
+    for (int t = 0; t < iters; ++t) {
+      F32Buffers b{};
+      b.s_in = loc(t); b.s_out = loc(t + 1);
+      b.x = tokens; b.pos = pos;
+      b.h = reinterpret_cast<float*>(ws + wl.h_off);
+      b.c = reinterpret_cast<float*>(ws + wl.c_off);
+      b.w1 = reinterpret_cast<const float*>(pw + pl.w1_off);
+      b.w2 = reinterpret_cast<const float*>(pw + pl.w2_off);
+      b.b1 = reinterpret_cast<const float*>(pw + pl.b1_off);
+      b.b2 = reinterpret_cast<const float*>(pw + pl.b2_off);
+      e = step_f32(g, b, st, &g_launches, &g_prof);
+      if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "fp32 step %d launch: %s", t, cudaGetErrorString(e));
+    }
+  }
+  g_err[0] = 0;
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, const float* bias, float* tokens, int batch, int height,
+                       int width, int patch, int dim, void* stream) {
+  if (!img || !weight || !bias || !tokens) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
+  if (batch < 1 || patch < 1 || dim < 1 || height < patch || width < patch || height % patch || width % patch)
+    return fail(GLOM_B200_ERR_INVALID, "image %dx%d is not a positive multiple of patch %d", height, width, patch);
+  DeviceInfo di{};
+  if (int r = device_info(&di)) return r;
+  g_launches = 0;
+  cudaError_t e = launch_tokenize(img, weight, bias, tokens, batch, height, width, patch, dim,
+                                  static_cast<cudaStream_t>(stream), &g_launches, &g_prof);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "tokenize launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_profile_begin(void) {
+  g_prof.enabled = true;
+  g_prof.used = 0;
+  g_prof.spans.clear();
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kind, int kinds) {
+  if (!ms_by_kind || !launches_by_kind || kinds < PROF_KINDS) return fail(GLOM_B200_ERR_INVALID, "need room for %d kinds", (int)PROF_KINDS);
+  for (int i = 0; i < kinds; ++i) { ms_by_kind[i] = 0.0; launches_by_kind[i] = 0; }
+  g_prof.enabled = false;
+  for (const Profiler::Span& s : g_prof.spans) {
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[s.b]);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof.ev[s.a], g_prof.ev[s.b]);
+    if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "profile events: %s", cudaGetErrorString(e));
+    ms_by_kind[s.kind] += ms;
+    launches_by_kind[s.kind] += 1;
+  }
+  g_prof.spans.clear();
+  g_prof.used = 0;
+  return 0;
+}
+
+}  // extern "C"

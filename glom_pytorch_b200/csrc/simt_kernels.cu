@@ -1,0 +1,399 @@
+// CUDA-core kernels: the fp32 precision path of the column update (exact-erf GELU, fp32
+// GEMMs, fp32 attention), weight packing, the state prologue of the bf16 path, and the
+// tokeniser.  The tensor-core path lives in tc_kernels.cu.
+//
+// Reference semantics (glom_pytorch/glom_pytorch.py): GroupedFeedForward :23-36,
+// ConsensusAttention :56-73, combine :128-129/:141-142, image_to_tokens :94-97.
+#include "engine.h"
+#include "ptx.cuh"
+
+namespace glom {
+
+// =====================================================================================
+// Weight packing (one-time per weight set)
+// =====================================================================================
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void pack_weights_kernel(int d, int L, const float* __restrict__ bu_w1, const float* __restrict__ bu_b1,
+                                    const float* __restrict__ bu_w2, const float* __restrict__ bu_b2,
+                                    const float* __restrict__ td_w1, const float* __restrict__ td_b1,
+                                    const float* __restrict__ td_w2, const float* __restrict__ td_b2,
+                                    T* __restrict__ w1p, T* __restrict__ w2p, float* __restrict__ b1p,
+                                    float* __restrict__ b2p) {
+  const int G = 2 * L - 1, h = 4 * d;
+  const size_t n_w1 = (size_t)G * h * d, n_w2 = (size_t)L * d * 8 * d;
+  const size_t n_b1 = (size_t)G * h, n_b2 = (size_t)L * d;
+  const size_t total = n_w1 + n_w2 + n_b1 + n_b2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_w1) {
+      const size_t row = i / d, k = i % d;
+      const int g = (int)(row / h), j = (int)(row % h), l = g >> 1;
+      const float v = (g & 1) ? td_w1[((size_t)l * h + j) * d + k] : bu_w1[((size_t)l * h + j) * d + k];
+      w1p[i] = cvt_out<T>(v);
+    } else if (i < n_w1 + n_w2) {
+      const size_t q = i - n_w1, row = q / (8 * (size_t)d), c = q % (8 * (size_t)d);
+      const int l = (int)(row / d);
+      float v;
+      if (c < (size_t)h) v = bu_w2[row * h + c];
+      else v = (l < L - 1) ? td_w2[row * h + (c - h)] : 0.0f;   // td rows of level l are rows l*d.. of td_w2
+      w2p[q] = cvt_out<T>(v);
+    } else if (i < n_w1 + n_w2 + n_b1) {
+      const size_t q = i - n_w1 - n_w2;
+      const int g = (int)(q / h), j = (int)(q % h), l = g >> 1;
+      b1p[q] = (g & 1) ? td_b1[(size_t)l * h + j] : bu_b1[(size_t)l * h + j];
+    } else {
+      const size_t q = i - n_w1 - n_w2 - n_b1;
+      const int l = (int)(q / d);
+      b2p[q] = bu_b2[q] + ((l < L - 1) ? td_b2[q] : 0.0f);
+    }
+  }
+}
+
+cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const float* bu_b1, const float* bu_w2,
+                        const float* bu_b2, const float* td_w1, const float* td_b1, const float* td_w2,
+                        const float* td_b2, void* packed, cudaStream_t st, int* launches) {
+  const PackedLayout pl = packed_layout(d, L, precision);
+  char* base = static_cast<char*>(packed);
+  float* b1p = reinterpret_cast<float*>(base + pl.b1_off);
+  float* b2p = reinterpret_cast<float*>(base + pl.b2_off);
+  const int grid = 148 * 8, block = 256;
+  if (precision == 1) {
+    pack_weights_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(
+        d, L, bu_w1, bu_b1, bu_w2, bu_b2, td_w1, td_b1, td_w2, td_b2,
+        reinterpret_cast<__nv_bfloat16*>(base + pl.w1_off), reinterpret_cast<__nv_bfloat16*>(base + pl.w2_off), b1p,
+        b2p);
+  } else {
+    pack_weights_kernel<float><<<grid, block, 0, st>>>(d, L, bu_w1, bu_b1, bu_w2, bu_b2, td_w1, td_b1, td_w2, td_b2,
+                                                        reinterpret_cast<float*>(base + pl.w1_off),
+                                                        reinterpret_cast<float*>(base + pl.w2_off), b1p, b2p);
+  }
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// State prologue of the bf16 path: S_0 -> (fp32 master copy), bf16 shadows, row norms
+// One warp per (row, level).  Replaces glom_pytorch.py:123-126 (+ the casts autocast inserts).
+// =====================================================================================
+__global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, const float* __restrict__ state_in,
+                                  const float* __restrict__ init_levels, const float* __restrict__ pos,
+                                  float* __restrict__ s32_dst, __nv_bfloat16* __restrict__ sb,
+                                  __nv_bfloat16* __restrict__ sp, float* __restrict__ nsq) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows * L) return;
+  const int r = warp / L, l = warp % L;
+  const float* src = state_in ? state_in + ((size_t)r * L + l) * d : init_levels + (size_t)l * d;
+  const float* p = pos + (size_t)(r % n) * d;
+  float ss = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    const size_t o = ((size_t)r * L + l) * d + c;
+    if (s32_dst) *reinterpret_cast<float4*>(s32_dst + o) = v;
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(sb + o) = pk;
+    if (l >= 1) {
+      const float4 q = *reinterpret_cast<const float4*>(p + c);
+      uint2 pq;
+      pq.x = pack_bf16x2(v.x + q.x, v.y + q.y);
+      pq.y = pack_bf16x2(v.z + q.z, v.w + q.w);
+      *reinterpret_cast<uint2*>(sp + ((size_t)r * (L - 1) + (l - 1)) * d + c) = pq;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane < nparts) nsq[((size_t)r * L + l) * nparts + lane] = (lane == 0) ? ss : 0.f;
+}
+
+__global__ void cast_bf16_kernel(size_t n4, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = pk;
+  }
+}
+
+cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* init_levels, const float* pos,
+                        const float* tokens, float* s32_dst, __nv_bfloat16* sb, __nv_bfloat16* sp,
+                        __nv_bfloat16* xb, float* nsq, cudaStream_t st, int* launches, Profiler* prof) {
+  ProfScope scope(prof, PROF_PREP, st);
+  const int warps = g.rows * g.L;
+  const int block = 256, grid = (warps * 32 + block - 1) / block;
+  prep_state_kernel<<<grid, block, 0, st>>>(g.rows, g.n, g.L, g.d, g.nparts, state_in, init_levels, pos, s32_dst, sb,
+                                            sp, nsq);
+  if (launches) ++*launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t n4 = (size_t)g.rows * g.d / 4;
+  cast_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, st>>>(n4, tokens, xb);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// S_0 materialisation for the fp32 path / return_all slab 0 (broadcast of init_levels or copy).
+__global__ void init_state_kernel(size_t total4, int L, int d, const float* __restrict__ state_in,
+                                  const float* __restrict__ init_levels, float* __restrict__ dst) {
+  const size_t ld4 = (size_t)L * d / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    reinterpret_cast<float4*>(dst)[i] = state_in ? reinterpret_cast<const float4*>(state_in)[i]
+                                                 : reinterpret_cast<const float4*>(init_levels)[i % ld4];
+  }
+}
+cudaError_t launch_broadcast_init(const Geometry& g, const float* state_in, const float* init_levels, float* dst,
+                                  cudaStream_t st, int* launches, Profiler* prof) {
+  ProfScope scope(prof, PROF_PREP, st);
+  const size_t total4 = (size_t)g.rows * g.L * g.d / 4;
+  const size_t want = (total4 + 255) / 256;
+  init_state_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, st>>>(total4, g.L, g.d, state_in, init_levels,
+                                                                                dst);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// fp32 GEMM  C[M x N] = A[M x K] . B[N x K]^T  with fused operand gathers / epilogues
+// 64x64 tile, BK = 16, 256 threads, 4x4 per thread.
+// =====================================================================================
+enum { MODE_FF1 = 0, MODE_FF2 = 1, MODE_TOK = 2 };
+
+struct SgemmParams {
+  int M, N, K;
+  int d, L, n, G;
+  const float* s;      // state (rows, L, d)
+  const float* x;      // tokens (rows, d)
+  const float* pos;    // (n, d)
+  const float* w;      // weights, row-major (out, K)
+  const float* bias;
+  float* out;          // FF1: H ; FF2: state t+1 ; TOK: tokens
+  const float* h;      // FF2 A operand
+  const float* c;      // FF2 consensus
+  // tokeniser
+  const float* img;
+  int Himg, Wimg, p;
+};
+
+template <int MODE>
+__device__ __forceinline__ float load_a(const SgemmParams& q, int z, int r, int k) {
+  if (MODE == MODE_FF1) {
+    if (z == 0) return q.x[(size_t)r * q.d + k];
+    const int l = z >> 1;
+    if (z & 1) return q.s[((size_t)r * q.L + l + 1) * q.d + k] + q.pos[(size_t)(r % q.n) * q.d + k];  // (:136)
+    return q.s[((size_t)r * q.L + l - 1) * q.d + k];                                               // (:134)
+  } else if (MODE == MODE_FF2) {
+    return q.h[(size_t)r * q.G * 4 * q.d + (size_t)2 * z * 4 * q.d + k];
+  } else {
+    // 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'  (:95)
+    const int p = q.p, wp = q.Wimg / p, hp = q.Himg / p;
+    const int b = r / (hp * wp), pr = r % (hp * wp), ph = pr / wp, pw = pr % wp;
+    const int c = k % 3, p12 = k / 3, p1 = p12 / p, p2 = p12 % p;
+    return q.img[(((size_t)b * 3 + c) * q.Himg + ph * p + p1) * q.Wimg + pw * p + p2];
+  }
+}
+template <int MODE>
+__device__ __forceinline__ float load_b(const SgemmParams& q, int z, int j, int k) {
+  if (MODE == MODE_FF1) return q.w[((size_t)z * 4 * q.d + j) * q.d + k];
+  if (MODE == MODE_FF2) return q.w[((size_t)z * q.d + j) * 8 * q.d + k];
+  return q.w[(size_t)j * q.K + k];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) sgemm_kernel(SgemmParams q) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int K = (MODE == MODE_FF2 && z == q.L - 1) ? q.K / 2 : q.K;   // top level has no top-down half (:137)
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int kk = i & 15, rr = i >> 4;
+      As[kk][rr] = (m0 + rr < q.M && k0 + kk < K) ? load_a<MODE>(q, z, m0 + rr, k0 + kk) : 0.f;
+      Bs[kk][rr] = (n0 + rr < q.N && k0 + kk < K) ? load_b<MODE>(q, z, n0 + rr, k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= q.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= q.N) continue;
+      if (MODE == MODE_FF1) {
+        const float v = acc[i][j] + q.bias[(size_t)z * 4 * q.d + c];
+        q.out[(size_t)r * q.G * 4 * q.d + (size_t)z * 4 * q.d + c] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+      } else if (MODE == MODE_FF2) {
+        const size_t o = ((size_t)r * q.L + z) * q.d + c;
+        const float sum = q.s[o] + (acc[i][j] + q.bias[(size_t)z * q.d + c]) + q.c[o];
+        q.out[o] = sum / ((z == q.L - 1) ? 3.0f : 4.0f);                                           // (:128-129, :142)
+      } else {
+        q.out[(size_t)r * q.N + c] = acc[i][j] + q.bias[c];
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// fp32 consensus attention (glom_pytorch.py:56-73).  Block = (image b, level l, 16 queries).
+// =====================================================================================
+constexpr int AQ = 16;
+__global__ void __launch_bounds__(256) attn_f32_kernel(int n, int L, int d, int attend_self, int mask_side,
+                                                       int mask_d2_max, const float* __restrict__ s,
+                                                       float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* qs = sm;                 // [AQ][d]
+  float* sim = sm + AQ * d;       // [AQ][n]
+  const int b = blockIdx.z, l = blockIdx.y, q0 = blockIdx.x * AQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t img = (size_t)b * n;
+  const float scale = rsqrtf((float)d);
+  for (int i = threadIdx.x; i < AQ * d; i += 256) {
+    const int qi = i / d, c = i % d;
+    qs[i] = (q0 + qi < n) ? s[((img + q0 + qi) * L + l) * d + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = warp; j < n; j += 8) {
+    const float* kr = s + ((img + j) * L + l) * d;
+    float dot[AQ];
+#pragma unroll
+    for (int i = 0; i < AQ; ++i) dot[i] = 0.f;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float kv = kr[c];
+      ss = fmaf(kv, kv, ss);
+#pragma unroll
+      for (int i = 0; i < AQ; ++i) dot[i] = fmaf(qs[i * d + c], kv, dot[i]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+#pragma unroll
+      for (int i = 0; i < AQ; ++i) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+    }
+    const float rinv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                          // F.normalize eps (:58)
+    if (lane < AQ) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < AQ; ++i) if (i == lane) v = dot[i];
+      const int qi = q0 + lane;
+      v = v * rinv * scale;                                                      // (:60)
+      if (!attend_self && qi == j) v = -5e-4f;                                   // (:62-65)
+      if (mask_side > 0 && qi < n) {                                             // (:67-69)
+        const int dh = qi / mask_side - j / mask_side, dw = qi % mask_side - j % mask_side;
+        if (dh * dh + dw * dw > mask_d2_max) v = -3.402823466e+38f;
+      }
+      sim[lane * n + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int qi = warp; qi < AQ; qi += 8) {                                        // softmax (:71)
+    float m = -3.402823466e+38f;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sim[qi * n + j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(sim[qi * n + j] - m);
+      sim[qi * n + j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) sim[qi * n + j] *= inv;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += 256) {                                   // P.V (:72)
+    float acc[AQ];
+#pragma unroll
+    for (int i = 0; i < AQ; ++i) acc[i] = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float v = s[((img + j) * L + l) * d + c];
+#pragma unroll
+      for (int i = 0; i < AQ; ++i) acc[i] = fmaf(sim[i * n + j], v, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < AQ; ++i)
+      if (q0 + i < n) out[((img + q0 + i) * L + l) * d + c] = acc[i];
+  }
+}
+
+cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, int* launches, Profiler* prof) {
+  // consensus
+  {
+    ProfScope scope(prof, PROF_ATTN, st);
+    const size_t smem = (size_t)(AQ * g.d + AQ * g.n) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    dim3 grid((g.n + AQ - 1) / AQ, g.L, g.B);
+    attn_f32_kernel<<<grid, 256, smem, st>>>(g.n, g.L, g.d, g.attend_self, g.mask_side, g.mask_d2_max, b.s_in, b.c);
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  SgemmParams q{};
+  q.d = g.d; q.L = g.L; q.n = g.n; q.G = g.G;
+  q.s = b.s_in; q.x = b.x; q.pos = b.pos;
+  // GEMM1 + GELU -> H
+  q.M = g.rows; q.N = 4 * g.d; q.K = g.d; q.w = b.w1; q.bias = b.b1; q.out = b.h;
+  {
+    ProfScope scope(prof, PROF_GEMM1, st);
+    dim3 grid((q.M + 63) / 64, (q.N + 63) / 64, g.G);
+    sgemm_kernel<MODE_FF1><<<grid, 256, 0, st>>>(q);
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  // GEMM2 + combine -> state t+1
+  q.N = g.d; q.K = 8 * g.d; q.w = b.w2; q.bias = b.b2; q.out = b.s_out; q.h = b.h; q.c = b.c;
+  {
+    ProfScope scope(prof, PROF_GEMM2, st);
+    dim3 grid((q.M + 63) / 64, (q.N + 63) / 64, g.L);
+    sgemm_kernel<MODE_FF2><<<grid, 256, 0, st>>>(q);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+  }
+}
+
+cudaError_t launch_tokenize(const float* img, const float* w, const float* bias, float* tokens, int B, int H, int W,
+                            int p, int d, cudaStream_t st, int* launches, Profiler* prof) {
+  ProfScope scope(prof, PROF_TOKENIZE, st);
+  SgemmParams q{};
+  q.M = B * (H / p) * (W / p); q.N = d; q.K = 3 * p * p;
+  q.w = w; q.bias = bias; q.out = tokens; q.img = img; q.Himg = H; q.Wimg = W; q.p = p;
+  dim3 grid((q.M + 63) / 64, (q.N + 63) / 64, 1);
+  sgemm_kernel<MODE_TOK><<<grid, 256, 0, st>>>(q);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace glom

@@ -1,0 +1,669 @@
+// Tensor-core (tcgen05 / TMEM / TMA) kernels of the GLOM column update for sm_100a.
+//
+//   gemm_kernel<0>  K1: H = gelu_erf(A_g . W1_g^T + b1_g)         all 2L-1 MLP groups, one launch
+//                       (GroupedFeedForward first Conv1d + GELU, glom_pytorch.py:29-30, calls :134/:136)
+//   gemm_kernel<1>  K2: S' = (S + C + [H_bu,l | H_td,l] . [W2bu_l | W2td_l]^T + b2) / c_l
+//                       (second Conv1d :31 of both nets, F.pad zero top level :137, combine :141-142)
+//   attn_kernel     K3: C = softmax_j(<S_i, S_j/|S_j|> d^-1/2, diag := -5e-4, radius mask) . S
+//                       (ConsensusAttention.forward :56-73)
+//
+// All three are warp-specialised: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one
+// lane), warp 2 = TMEM allocator, remaining warps = TMEM->register epilogue / softmax.
+// Operands are staged by TMA into 128B-swizzled shared memory; accumulators live in TMEM.
+#include "engine.h"
+#include "ptx.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace glom {
+
+constexpr int BM = 128;            // UMMA M (rows of the state per tile)
+constexpr int BK = 64;             // bf16 elements per 128-byte swizzle row
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+
+// =====================================================================================
+// K1 / K2: persistent grouped GEMM with fused epilogues
+// =====================================================================================
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int GEMM_EPI_THREADS = 256;
+
+struct GemmParams {
+  int rows, d, L, n, G;
+  int num_m, num_n, num_tiles;
+  const float* bias;
+  // K1
+  __nv_bfloat16* h_out;
+  // K2
+  const float* s32_in;
+  const __nv_bfloat16* c_in;
+  const float* pos;
+  float* s32_out;
+  __nv_bfloat16* sb_out;
+  __nv_bfloat16* sp_out;
+  float* nsq_out;
+  int nparts;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator stages (power of two >= 32)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
+};
+
+struct TileInfo {
+  int z;        // K1: group g ; K2: level l
+  int m_blk, n_blk;
+  int num_kb;   // K blocks of 64
+};
+
+template <int MODE>
+__device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
+  TileInfo t;
+  t.n_blk = tile % p.num_n;
+  const int r = tile / p.num_n;
+  t.m_blk = r % p.num_m;
+  t.z = r / p.num_m;
+  if (MODE == 0) t.num_kb = p.d / BK;
+  else t.num_kb = ((t.z == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;   // top level: no top-down half (:137)
+  return t;
+}
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows, d)        K2: H (rows, G*4d)
+            const __grid_constant__ CUtensorMap map_a1,   // K1: state shadow Sb (rows, L*d)
+            const __grid_constant__ CUtensorMap map_a2,   // K1: Sb[:,1:]+pos shadow Sp (rows, (L-1)*d)
+            const __grid_constant__ CUtensorMap map_b,    // K1: W1p (G*4d, d)              K2: W2p (L*d, 8d)
+            const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b);
+    if (MODE == 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile<MODE>(p, tile);
+        const CUtensorMap* amap;
+        int a_col, b_row;
+        if (MODE == 0) {
+          const int l = t.z >> 1;
+          if (t.z == 0) { amap = &map_a0; a_col = 0; }                        // bottom-up level 0 reads the tokens (:132)
+          else if (t.z & 1) { amap = &map_a2; a_col = l * p.d; }              // top-down l reads S[l+1]+pos (:136)
+          else { amap = &map_a1; a_col = (l - 1) * p.d; }                     // bottom-up l reads S[l-1]   (:134)
+          b_row = t.z * 4 * p.d + t.n_blk * BN;
+        } else {
+          amap = &map_a0; a_col = 2 * t.z * 4 * p.d;
+          b_row = t.z * p.d + t.n_blk * BN;
+        }
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, amap, &full_bar[stage], a_col + kb * BK, t.m_blk * BM);
+          tma_load_2d(sa + A_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile<MODE>(p, tile);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp - 4;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                  // column half of the tile
+    constexpr int HALF_COLS = BN / 2;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileInfo t = decode_tile<MODE>(p, tile);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+      const int row = t.m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.rows;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * HALF_COLS);
+      float sumsq = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        const int col = t.n_blk * BN + half * HALF_COLS + c0;    // column inside the group / level
+        if (MODE == 0) {
+          const float* bias = p.bias + (size_t)t.z * 4 * p.d + col;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + i));
+            const float x0 = gelu_erf_fast(__uint_as_float(v[i + 0]) + b4.x);
+            const float x1 = gelu_erf_fast(__uint_as_float(v[i + 1]) + b4.y);
+            const float x2 = gelu_erf_fast(__uint_as_float(v[i + 2]) + b4.z);
+            const float x3 = gelu_erf_fast(__uint_as_float(v[i + 3]) + b4.w);
+            pk[i / 2] = pack_bf16x2(x0, x1);
+            pk[i / 2 + 1] = pack_bf16x2(x2, x3);
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.h_out + (size_t)row * p.G * 4 * p.d + (size_t)t.z * 4 * p.d + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        } else {
+          if (row_ok && col < p.d) {
+            const int l = t.z;
+            const size_t o = ((size_t)row * p.L + l) * p.d + col;
+            const float divisor = (l == p.L - 1) ? 3.0f : 4.0f;                  // (:128-129)
+            const float* bias = p.bias + (size_t)l * p.d + col;
+            const float* posr = p.pos + (size_t)(row % p.n) * p.d + col;
+            const float4* s4 = reinterpret_cast<const float4*>(p.s32_in + o);
+            const uint4* c4 = reinterpret_cast<const uint4*>(p.c_in + o);
+            float4* so4 = reinterpret_cast<float4*>(p.s32_out + o);
+            uint4* sb4 = reinterpret_cast<uint4*>(p.sb_out + o);
+            uint4* sp4 = (l >= 1) ? reinterpret_cast<uint4*>(p.sp_out + ((size_t)row * (p.L - 1) + (l - 1)) * p.d + col)
+                                  : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const float4 sa = s4[i / 4], sb = s4[i / 4 + 1];
+              const uint4 cc = c4[i / 8];
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + i));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+              float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+              const uint32_t cw[4] = {cc.x, cc.y, cc.z, cc.w};
+              float o8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float cv = __uint_as_float((j & 1) ? (cw[j >> 1] & 0xFFFF0000u) : (cw[j >> 1] << 16));
+                const float mlp = __uint_as_float(v[i + j]) + bv[j];             // BU + TD (+ both second biases)
+                o8[j] = ((sv[j] + mlp) + cv) / divisor;                          // (:141-142)
+                sumsq = fmaf(o8[j], o8[j], sumsq);
+              }
+              so4[i / 4] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+              so4[i / 4 + 1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+              sb4[i / 8] = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]),
+                                      pack_bf16x2(o8[6], o8[7]));
+              if (sp4) {
+                const float4 pa = __ldg(reinterpret_cast<const float4*>(posr + i));
+                const float4 pb = __ldg(reinterpret_cast<const float4*>(posr + i + 4));
+                sp4[i / 8] = make_uint4(pack_bf16x2(o8[0] + pa.x, o8[1] + pa.y), pack_bf16x2(o8[2] + pa.z, o8[3] + pa.w),
+                                        pack_bf16x2(o8[4] + pb.x, o8[5] + pb.y), pack_bf16x2(o8[6] + pb.z, o8[7] + pb.w));
+              }
+            }
+          }
+        }
+      }
+      if (MODE == 1 && row_ok)
+        p.nsq_out[((size_t)row * p.L + t.z) * p.nparts + t.n_blk * 2 + half] = sumsq;
+      tc_fence_before_sync();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =====================================================================================
+// K3: consensus attention.  CTA = (query tile of 128, level l, image b).
+//   phase 1: S = Q K^T per key block (<= 256 keys) over d, fp32 in TMEM; softmax warps turn each
+//            block into unnormalised bf16 probabilities P in shared memory (UMMA A-operand layout)
+//   phase 2: O = P V per 256-wide slice of d (V read MN-major straight from the state shadow),
+//            scaled by 1/rowsum and written as bf16 C.
+// =====================================================================================
+constexpr int ATTN_THREADS = 256;
+constexpr int ATTN_SM_THREADS = 128;
+constexpr int ATTN_MAX_KB = 4;
+constexpr uint32_t ATTN_STAGE_BYTES = A_STAGE_BYTES + 256 * 128;   // Q tile + K block (or V slice)
+
+struct AttnParams {
+  int n, L, d;
+  int attend_self, mask_side, mask_d2_max;
+  int n_pad16, n_pad64, nkb, nchunk;   // key padding, key blocks (<=256), 64-key chunks
+  int kbox_rows;                       // rows fetched per K box
+  int num_stages;
+  int nparts;
+  const float* nsq;                    // (rows, L, nparts) squared-norm partials of the state
+  __nv_bfloat16* c_out;                // (rows, L, d)
+  float scale;                         // d^-1/2 (:60)
+};
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64, 128, 1)
+            const __grid_constant__ CUtensorMap map_k,    // box (64, kbox_rows, 1)
+            const __grid_constant__ CUtensorMap map_v,    // box (64, 64, 1)
+            const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* p_smem = smem;                                                  // nchunk x [128 x 64] bf16, SW128
+  uint8_t* stages = p_smem + (size_t)p.nchunk * A_STAGE_BYTES;
+  float* rs = reinterpret_cast<float*>(stages + (size_t)p.num_stages * ATTN_STAGE_BYTES);   // [n_pad16]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rs + p.n_pad16);
+  uint64_t* empty_bar = full_bar + p.num_stages;
+  uint64_t* afull_bar = empty_bar + p.num_stages;
+  uint64_t* aempty_bar = afull_bar + 2;
+  uint64_t* pready_bar = aempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pready_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, l = blockIdx.y, b = blockIdx.z;
+  const int npass = (p.d + 255) / 256;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], ATTN_SM_THREADS); }
+    mbar_init(pready_bar, ATTN_SM_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int dc = 0; dc < p.d / BK; ++dc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = stages + (size_t)stage * ATTN_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (uint32_t)p.kbox_rows * 128u);
+          tma_load_3d(s, &map_q, &full_bar[stage], l * p.d + dc * BK, q0, b);
+          tma_load_3d(s + A_STAGE_BYTES, &map_k, &full_bar[stage], l * p.d + dc * BK, kb * 256, b);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int ps = 0; ps < npass; ++ps) {
+        const int wd = min(256, p.d - ps * 256);
+        for (int kc = 0; kc < p.nchunk; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = stages + (size_t)stage * ATTN_STAGE_BYTES + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(wd / 64) * 8192u);
+          for (int i = 0; i < wd / 64; ++i)
+            tma_load_3d(s + i * 8192, &map_v, &full_bar[stage], l * p.d + ps * 256 + i * 64, kc * 64, b);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int job = 0;
+      // phase 1: S_kb = Q K_kb^T
+      for (int kb = 0; kb < p.nkb; ++kb, ++job) {
+        const int w = min(256, p.n_pad16 - kb * 256);
+        const uint32_t idesc = umma_idesc_bf16(BM, w, 0, 0);
+        const int buf = job & 1;
+        mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int dc = 0; dc < p.d / BK; ++dc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(stages + (size_t)stage * ATTN_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
+                      idesc, (dc | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&afull_bar[buf]);
+      }
+      // phase 2: O = P V   (A = P from smem, K-major; B = V slice, MN-major)
+      mbar_wait(pready_bar, 0);
+      tc_fence_after_sync();
+      for (int ps = 0; ps < npass; ++ps, ++job) {
+        const int wd = min(256, p.d - ps * 256);
+        const uint32_t idesc = umma_idesc_bf16(BM, wd, 0, 1);
+        const int buf = job & 1;
+        mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int kc = 0; kc < p.nchunk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(p_smem + (size_t)kc * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(stages + (size_t)stage * ATTN_STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                      umma_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&afull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output warps
+    const int quad = warp & 3;
+    const int t = quad * 32 + lane;          // query row inside the tile == TMEM lane
+    const int qi = q0 + t;
+    const int tid = threadIdx.x - 128;
+    const size_t img_row0 = (size_t)b * p.n;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float NEG_INF = __int_as_float(0xff800000);
+
+    // per-key scale  d^-1/2 / max(|S_j|, 1e-12)   (F.normalize eps, :58)
+    for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS) {
+      float v = 0.f;
+      if (j < p.n) {
+        const float* ns = p.nsq + ((img_row0 + j) * p.L + l) * p.nparts;
+        float ss = 0.f;
+        for (int i = 0; i < p.nparts; ++i) ss += ns[i];
+        v = p.scale / fmaxf(sqrtf(ss), 1e-12f);
+      }
+      rs[j] = v;
+    }
+    named_bar_sync(1, ATTN_SM_THREADS);
+
+    const int qh = (p.mask_side > 0) ? qi / p.mask_side : 0, qw = (p.mask_side > 0) ? qi % p.mask_side : 0;
+    auto logit = [&](uint32_t raw, int j) -> float {
+      float sv = __uint_as_float(raw) * rs[j];                                      // (:60)
+      if (!p.attend_self && j == qi) sv = -5e-4f;                                   // (:62-65)
+      bool masked = j >= p.n;
+      if (p.mask_side > 0) {                                                        // (:67-69)
+        const int dh = qh - j / p.mask_side, dw = qw - j % p.mask_side;
+        masked |= (dh * dh + dw * dw > p.mask_d2_max);
+      }
+      return masked ? NEG_INF : sv;
+    };
+
+    float m_run = NEG_INF, l_run = 0.f;
+    float m_used[ATTN_MAX_KB];
+    int job = 0;
+    for (int kb = 0; kb < p.nkb; ++kb, ++job) {
+      const int w = min(256, p.n_pad16 - kb * 256);
+      const int buf = job & 1;
+      mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+      float bm = NEG_INF;
+      for (int c0 = 0; c0 < w; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bm = fmaxf(bm, logit(v[i], kb * 256 + c0 + i));
+      }
+      const float m_new = fmaxf(m_run, bm);
+      const float m_safe = (m_new == NEG_INF) ? 0.f : m_new;
+      l_run *= (m_run == NEG_INF) ? 0.f : ex2_approx((m_run - m_safe) * LOG2E);
+      for (int c0 = 0; c0 < w; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float e0 = ex2_approx((logit(v[i], kb * 256 + c0 + i) - m_safe) * LOG2E);
+          const float e1 = ex2_approx((logit(v[i + 1], kb * 256 + c0 + i + 1) - m_safe) * LOG2E);
+          l_run += e0 + e1;
+          pk[i / 2] = pack_bf16x2(e0, e1);
+        }
+        const int key = kb * 256 + c0;                     // multiple of 16
+        uint8_t* rowp = p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128;
+        const int ch = (key & 63) >> 3;                    // 16-byte chunk index inside the 128-byte row (even)
+        *reinterpret_cast<uint4*>(rowp + (((ch) ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (t & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      m_used[kb] = m_safe;
+      m_run = m_new;
+      tc_fence_before_sync();
+      mbar_arrive(&aempty_bar[buf]);
+    }
+    const float m_fin = (m_run == NEG_INF) ? 0.f : m_run;
+    // bring every block's probabilities onto the final stabiliser; zero the K-padding keys
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      if (m_used[kb] == m_fin) continue;
+      const float f = ex2_approx((m_used[kb] - m_fin) * LOG2E);
+      const int w = min(256, p.n_pad16 - kb * 256);
+      for (int c0 = 0; c0 < w; c0 += 8) {
+        const int key = kb * 256 + c0;
+        uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
+                                              ((((key & 63) >> 3) ^ (t & 7)) << 4));
+        uint4 u = *ptr;
+        uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = __uint_as_float(wv[i] << 16) * f, hi = __uint_as_float(wv[i] & 0xFFFF0000u) * f;
+          wv[i] = pack_bf16x2(lo, hi);
+        }
+        *ptr = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+    }
+    for (int key = p.n_pad16; key < p.n_pad64; key += 8) {
+      uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
+                                            ((((key & 63) >> 3) ^ (t & 7)) << 4));
+      *ptr = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(pready_bar);
+
+    const float inv_l = 1.0f / l_run;
+    for (int ps = 0; ps < npass; ++ps, ++job) {
+      const int wd = min(256, p.d - ps * 256);
+      const int buf = job & 1;
+      mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+      for (int c0 = 0; c0 < wd; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (qi < p.n) {
+          uint4* dst = reinterpret_cast<uint4*>(p.c_out + ((img_row0 + qi) * p.L + l) * p.d + ps * 256 + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l),
+                                pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l),
+                                pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l),
+                                pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l));
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&aempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================
+// Host side: tensor maps + launches for one Jacobi step
+// =====================================================================================
+static bool encode_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, char* err, size_t errlen,
+                       const char* what) {
+  cuuint64_t gd[3]; cuuint64_t gs[2]; cuuint32_t bx[3]; cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return false;
+  }
+  return true;
+}
+
+static bool map2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                  char* err, size_t errlen, const char* what) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {cols * 2};
+  const uint32_t box[2] = {(uint32_t)BK, box_rows};
+  return encode_map(enc, m, base, 2, dims, strides, box, err, errlen, what);
+}
+
+template <int MODE, int BN>
+static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
+                               const GemmParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  gemm_kernel<MODE, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, a2, bm, p);
+  return cudaGetLastError();
+}
+
+int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
+              char* err, size_t errlen, Profiler* prof) {
+  const int d = g.d, L = g.L, n = g.n, rows = g.rows;
+  // ---------------- K3: consensus attention -> C
+  {
+    AttnParams ap{};
+    ap.n = n; ap.L = L; ap.d = d;
+    ap.attend_self = g.attend_self; ap.mask_side = g.mask_side; ap.mask_d2_max = g.mask_d2_max;
+    ap.n_pad16 = (n + 15) / 16 * 16;
+    ap.n_pad64 = (n + 63) / 64 * 64;
+    ap.nkb = (ap.n_pad16 + 255) / 256;
+    ap.nchunk = ap.n_pad64 / 64;
+    ap.kbox_rows = ap.n_pad16 < 256 ? ap.n_pad16 : 256;
+    ap.nparts = g.nparts;
+    ap.nsq = b.nsq_in;
+    ap.c_out = b.c;
+    ap.scale = 1.0f / sqrtf((float)d);
+    if (ap.nkb > ATTN_MAX_KB) { snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n); return -1; }
+    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + (size_t)ap.n_pad16 * 4 + 256;
+    const size_t max_smem = 227 * 1024;
+    int stages = 4;
+    while (stages > 0 && fixed + (size_t)stages * ATTN_STAGE_BYTES > max_smem) --stages;
+    if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
+    ap.num_stages = stages;
+    const size_t smem = fixed + (size_t)stages * ATTN_STAGE_BYTES;
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e)); return -3; }
+      configured = smem;
+    }
+    CUtensorMap mq, mk, mv;
+    const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
+    const uint64_t strides[2] = {(uint64_t)L * d * 2, (uint64_t)n * L * d * 2};
+    const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.kbox_rows, 1},
+                   boxv[3] = {(uint32_t)BK, 64, 1};
+    if (!encode_map(enc, &mq, b.sb_in, 3, dims, strides, boxq, err, errlen, "attn.q")) return -3;
+    if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
+    if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
+    dim3 grid((n + BM - 1) / BM, L, g.B);
+    ProfScope scope(prof, PROF_ATTN, st);
+    attn_kernel<<<grid, ATTN_THREADS, smem, st>>>(mq, mk, mv, ap);
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  }
+  // ---------------- K1: grouped GEMM1 + bias + GELU -> H
+  CUtensorMap mh;
+  if (!map2d(enc, &mh, b.h, rows, (uint64_t)g.G * 4 * d, BM, err, errlen, "H")) return -3;
+  {
+    CUtensorMap mx, msb, msp, mw1;
+    if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
+    if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
+    if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
+    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 256, err, errlen, "W1p")) return -3;
+    GemmParams p{};
+    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+    p.num_m = (rows + BM - 1) / BM; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
+    p.bias = b.b1; p.h_out = b.h;
+    ProfScope scope(prof, PROF_GEMM1, st);
+    cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
+  }
+  // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)
+  {
+    CUtensorMap mw2;
+    if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2, err, errlen, "W2p")) return -3;
+    GemmParams p{};
+    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+    p.num_m = (rows + BM - 1) / BM; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
+    p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+    p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+    cudaError_t e;
+    ProfScope scope(prof, PROF_GEMM2, st);
+    if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
+    else if (g.bn2 == 128) e = launch_gemm<1, 128>(mh, mh, mh, mw2, p, num_sms, st);
+    else e = launch_gemm<1, 64>(mh, mh, mh, mw2, p, num_sms, st);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
+  }
+  return 0;
+}
+
+}  // namespace glom

@@ -1,0 +1,219 @@
+"""Drop-in `Glom` for lucidrains/glom-pytorch whose column-update loop runs on the B200 engine.
+
+Mirrors the reference's public surface (glom_pytorch/glom_pytorch.py):
+  * ``Glom.__init__(*, dim, levels, image_size, patch_size, consensus_self,
+    local_consensus_radius)``  (:78-87), attribute ``self.levels`` (:92);
+  * ``state_dict()`` keys/shapes: ``init_levels``, ``image_to_tokens.1.{weight,bias}``,
+    ``pos_emb.weight``, ``bottom_up.net.{1,3}.{weight,bias}``, ``top_down.net.{1,3}.{weight,bias}``,
+    ``attention.non_local_mask`` (radius > 0 only)  -- so ``load_state_dict(ref.state_dict())`` works;
+  * ``forward(img, iters=None, levels=None, return_all=False)`` (:110): ``iters=None -> 2L`` (:112),
+    ``iters=0`` returns S_0, output ``(B, n, L, d)`` or ``(T+1, B, n, L, d)`` fp32.
+
+What differs: the loop body (:131-145) plus GroupedFeedForward.forward / ConsensusAttention.forward is
+one call into ``libglom_b200.so`` (C ABI in include/glom_b200.h).  CUDA sm_100 only, forward only:
+there is no CPU / eager fallback -- inputs on other devices, or inputs that need autograd, raise.
+
+Engine-only knob (keyword-only, additive): ``precision`` = ``"bf16"`` (default; tcgen05 tensor cores,
+bf16 operands, fp32 accumulate and fp32 state -- the arithmetic of the reference under
+``torch.autocast(dtype=torch.bfloat16)``) or ``"fp32"`` (CUDA-core path matching the reference's fp32
+forward to ~1e-5).
+"""
+from math import sqrt
+
+import torch
+from torch import nn
+
+from . import _native
+
+
+class _Patchify(nn.Module):
+    """Parameter-free placeholder at index 0 so the Linear keeps the key ``image_to_tokens.1.*``
+    (the reference has an einops Rearrange there, glom_pytorch.py:95)."""
+
+    def __init__(self, patch_size):
+        super().__init__()
+        self.patch_size = patch_size
+
+    def forward(self, img):
+        b, c, h, w = img.shape
+        p = self.patch_size
+        x = img.reshape(b, c, h // p, p, w // p, p).permute(0, 2, 4, 3, 5, 1)   # b h w p1 p2 c
+        return x.reshape(b, (h // p) * (w // p), p * p * c)
+
+
+class GroupedFeedForward(nn.Module):
+    """Parameter container with the reference's layout (glom_pytorch.py:23-36): two grouped 1x1
+    Conv1d at ``net.1`` and ``net.3``.  The engine consumes the weights repacked; this module has
+    no forward of its own."""
+
+    def __init__(self, *, dim, groups, mult=4):
+        super().__init__()
+        total = dim * groups
+        self.net = nn.Sequential(
+            nn.Identity(),
+            nn.Conv1d(total, total * mult, 1, groups=groups),
+            nn.GELU(),
+            nn.Conv1d(total * mult, total, 1, groups=groups),
+            nn.Identity(),
+        )
+
+    def forward(self, *_):
+        raise RuntimeError("GroupedFeedForward runs inside the fused B200 column update; call Glom.forward")
+
+
+class ConsensusAttention(nn.Module):
+    """Holds attend_self / radius and the ``non_local_mask`` buffer (glom_pytorch.py:39-54)."""
+
+    def __init__(self, num_patches_side, attend_self=True, local_consensus_radius=0):
+        super().__init__()
+        self.attend_self = attend_self
+        self.local_consensus_radius = local_consensus_radius
+        self.num_patches_side = num_patches_side
+        if local_consensus_radius > 0:
+            ar = torch.arange(num_patches_side)
+            hh, ww = torch.meshgrid(ar, ar, indexing="ij")
+            co = torch.stack((hh.reshape(-1), ww.reshape(-1)), -1).float()     # (h w) c
+            dist = torch.cdist(co, co)
+            self.register_buffer("non_local_mask", (dist > local_consensus_radius)[None])
+
+    def forward(self, *_):
+        raise RuntimeError("ConsensusAttention runs inside the fused B200 column update; call Glom.forward")
+
+    def mask_params(self, n):
+        """(mask_side, mask_d2_max) for the engine's analytic mask, derived from the buffer so a
+        loaded state_dict is honoured; raises if the buffer is not a radial mask on the grid."""
+        if self.local_consensus_radius <= 0:
+            return 0, 0
+        side = self.num_patches_side
+        mask = self.non_local_mask[0]
+        if n != side * side:
+            raise RuntimeError(f"local_consensus_radius needs n == num_patches ({side * side}), got {n} "
+                               "(the reference's masked_fill_ fails the same way)")
+        key = getattr(self, "_mask_key", None)
+        if key is None or key[0] is not self.non_local_mask:
+            ar = torch.arange(side, device=mask.device)
+            hh, ww = torch.meshgrid(ar, ar, indexing="ij")
+            co = torch.stack((hh.reshape(-1), ww.reshape(-1)), -1)
+            d2 = ((co[:, None, :] - co[None, :, :]) ** 2).sum(-1)
+            kept = d2[~mask]
+            d2_max = int(kept.max().item()) if kept.numel() else -1
+            if not torch.equal(d2 > d2_max, mask):
+                raise RuntimeError("attention.non_local_mask is not a radius mask on the patch grid")
+            self._mask_key = (self.non_local_mask, d2_max)
+        return side, self._mask_key[1]
+
+
+class Glom(nn.Module):
+    def __init__(self, *, dim=512, levels=6, image_size=224, patch_size=14, consensus_self=False,
+                 local_consensus_radius=0, precision="bf16"):
+        super().__init__()
+        if precision not in _native.PRECISION:
+            raise ValueError(f"precision must be one of {sorted(_native.PRECISION)}")
+        num_patches_side = image_size // patch_size
+        num_patches = num_patches_side ** 2
+        self.levels = levels
+        self.dim = dim
+        self.patch_size = patch_size
+        self.precision = precision
+
+        # creation order matches the reference (:94-108) so seeded default init is identical
+        self.image_to_tokens = nn.Sequential(_Patchify(patch_size), nn.Linear(patch_size ** 2 * 3, dim))
+        self.pos_emb = nn.Embedding(num_patches, dim)
+        self.init_levels = nn.Parameter(torch.randn(levels, dim))
+        self.bottom_up = GroupedFeedForward(dim=dim, groups=levels)
+        self.top_down = GroupedFeedForward(dim=dim, groups=levels - 1)
+        self.attention = ConsensusAttention(num_patches_side, attend_self=consensus_self,
+                                            local_consensus_radius=local_consensus_radius)
+        self._packed = None          # (key, tensor)
+        self._workspace = None       # grown on demand, reused across calls (video continuation)
+        self.use_native_tokenizer = True
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _mlp_params(self):
+        return (self.bottom_up.net[1].weight, self.bottom_up.net[1].bias,
+                self.bottom_up.net[3].weight, self.bottom_up.net[3].bias,
+                self.top_down.net[1].weight, self.top_down.net[1].bias,
+                self.top_down.net[3].weight, self.top_down.net[3].bias)
+
+    def _packed_weights(self, cfg, device, stream):
+        params = self._mlp_params()
+        key = (self.precision, device, tuple((p.data_ptr(), p._version) for p in params))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        srcs = []
+        for p in params:
+            t = p.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            srcs.append(t)
+        nbytes = _native.packed_weight_bytes(cfg)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _native.pack_weights(cfg, [t.data_ptr() for t in srcs], packed.data_ptr(), nbytes, stream)
+        self._packed = (key, packed)
+        return packed
+
+    def _get_workspace(self, nbytes, device):
+        ws = self._workspace
+        if ws is None or ws.device != device or ws.numel() < nbytes:
+            self._workspace = ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return ws
+
+    def engine_cfg(self, n):
+        side, d2 = self.attention.mask_params(n)
+        return _native.make_cfg(self.dim, self.levels, n, self.attention.attend_self, side, d2, self.precision)
+
+    def tokens(self, img):
+        """image_to_tokens (:114) -- the engine's fused patchify+Linear kernel, fp32."""
+        lin = self.image_to_tokens[1]
+        b, c, h, w = img.shape
+        p = self.patch_size
+        if c != 3 or h % p or w % p:
+            raise RuntimeError(f"image {tuple(img.shape)} is not (B, 3, H, W) with H, W multiples of {p}")
+        if not self.use_native_tokenizer:
+            return lin(self.image_to_tokens[0](img.float())).contiguous()
+        img = img.float().contiguous()
+        out = torch.empty(b, (h // p) * (w // p), self.dim, dtype=torch.float32, device=img.device)
+        wt, bs = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+        _native.tokenize(img.data_ptr(), wt.data_ptr(), bs.data_ptr(), out.data_ptr(), b, h, w, p, self.dim,
+                         torch.cuda.current_stream(img.device).cuda_stream)
+        self._tok_launches = _native.last_launch_count()
+        return out
+
+    # ------------------------------------------------------------------ the reference's forward (:110)
+    def forward(self, img, iters=None, levels=None, return_all=False):
+        if not img.is_cuda:
+            raise RuntimeError("glom_pytorch_b200.Glom runs on CUDA sm_100 only (no CPU fallback); "
+                               "move the module and inputs to a B200")
+        if torch.is_grad_enabled() and (img.requires_grad or (levels is not None and levels.requires_grad)
+                                        or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("the B200 column-update engine is forward-only: call it under torch.no_grad() "
+                               "(or freeze the parameters); autograd through the loop is not implemented")
+        device = img.device
+        b = img.shape[0]
+        iters = self.levels * 2 if iters is None else int(iters)             # (:112)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            tokens = self.tokens(img)                                        # (:114)
+            n = tokens.shape[1]
+            if n > self.pos_emb.num_embeddings:
+                raise IndexError(f"{n} patches exceed pos_emb size {self.pos_emb.num_embeddings}")   # (:117)
+            pos = self.pos_emb.weight.detach()[:n].float().contiguous()
+            state_in = None
+            if levels is not None:                                           # (:123)
+                if tuple(levels.shape) != (b, n, self.levels, self.dim):
+                    raise RuntimeError(f"levels must have shape {(b, n, self.levels, self.dim)}, "
+                                       f"got {tuple(levels.shape)}")
+                state_in = levels.detach().to(device=device, dtype=torch.float32).contiguous()
+            init = self.init_levels.detach().float().contiguous()
+            cfg = self.engine_cfg(n)
+            packed = self._packed_weights(cfg, device, stream)
+            shape = (b, n, self.levels, self.dim)
+            out = torch.empty(((iters + 1,) + shape) if return_all else shape, dtype=torch.float32, device=device)
+            ws_bytes = _native.workspace_bytes(cfg, b, iters, return_all)
+            ws = self._get_workspace(ws_bytes, device)
+            _native.forward(cfg, packed.data_ptr(), tokens.data_ptr(), pos.data_ptr(),
+                            None if state_in is None else state_in.data_ptr(), init.data_ptr(),
+                            out.data_ptr(), b, iters, return_all, ws.data_ptr(), ws.numel(), stream)
+            self.last_launches = _native.last_launch_count() + getattr(self, "_tok_launches", 0)
+        return out

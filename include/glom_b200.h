@@ -1,0 +1,141 @@
+/*
+ * glom_b200.h -- C ABI of the B200-native GLOM column-update engine (libglom_b200.so).
+ *
+ * The reference (lucidrains/glom-pytorch) has no FFI: its hot path is the Python loop
+ * glom_pytorch/glom_pytorch.py:131-145 calling GroupedFeedForward (:23-36) and
+ * ConsensusAttention (:38-73).  This header is the boundary a maintainer would bind
+ * instead of that loop (ctypes stub in INTEGRATION.md).  Conventions:
+ *
+ *   - plain C symbols, POD structs with a leading struct_size, no torch types;
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator);
+ *     the library never allocates device memory, never synchronises the stream and
+ *     never throws: 0 on success, a negative glom_b200_status otherwise, text via
+ *     glom_b200_last_error() (thread-local);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*) of the CURRENT
+ *     device (caller does cudaSetDevice / torch.cuda.device);
+ *   - state layout is the reference's: (B, n, L, d) contiguous, d fastest, fp32
+ *     (the reference carries the state in fp32 even under autocast).
+ */
+#ifndef GLOM_B200_H_
+#define GLOM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLOM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GLOM_B200_API __attribute__((visibility("default")))
+#else
+#define GLOM_B200_API
+#endif
+
+typedef enum glom_b200_status {
+  GLOM_B200_OK = 0,
+  GLOM_B200_ERR_INVALID = -1,     /* bad argument / unsupported shape              */
+  GLOM_B200_ERR_WORKSPACE = -2,   /* workspace or packed buffer too small          */
+  GLOM_B200_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed             */
+  GLOM_B200_ERR_DEVICE = -4       /* device is not sm_100 (no CPU / other-arch fallback) */
+} glom_b200_status;
+
+typedef enum glom_b200_precision {
+  GLOM_B200_FP32 = 0,  /* CUDA-core fp32 path: matches the reference's fp32 forward     */
+  GLOM_B200_BF16 = 1   /* tcgen05 path: bf16 operands, fp32 accumulate, fp32 state --
+                          the arithmetic of the reference under torch.autocast(bf16)     */
+} glom_b200_precision;
+
+/* Static description of one Glom module + one call geometry.
+ * Mirrors Glom.__init__ kwargs (glom_pytorch.py:78-87) and ConsensusAttention (:39-54). */
+typedef struct glom_b200_cfg {
+  uint32_t struct_size;   /* = sizeof(glom_b200_cfg)                                     */
+  int32_t dim;            /* d                                                           */
+  int32_t levels;         /* L  (>= 2: the reference cannot build top_down for L == 1)    */
+  int32_t n;              /* columns (patches) of THIS call, n <= num_patches (:115)     */
+  int32_t attend_self;    /* consensus_self (:85); 0 => diagonal logit := -5e-4 (:11)    */
+  int32_t mask_side;      /* patches per grid row for the radius mask; 0 => no mask      */
+  int32_t mask_d2_max;    /* logits with (dh^2+dw^2) > mask_d2_max are masked (:44-54,
+                             :67-69).  The host derives it from non_local_mask.          */
+  int32_t precision;      /* glom_b200_precision                                         */
+} glom_b200_cfg;
+
+/* Device pointers to the reference's parameters in state_dict layout (fp32, contiguous):
+ *   bottom_up.net.1.weight (L*4d, d, 1)   .bias (L*4d)      glom_pytorch.py:29
+ *   bottom_up.net.3.weight (L*d, 4d, 1)   .bias (L*d)       glom_pytorch.py:31
+ *   top_down.*  same with L-1 groups                         glom_pytorch.py:105   */
+typedef struct glom_b200_weights_ref {
+  uint32_t struct_size;
+  const float* bu_w1; const float* bu_b1; const float* bu_w2; const float* bu_b2;
+  const float* td_w1; const float* td_b1; const float* td_w2; const float* td_b2;
+} glom_b200_weights_ref;
+
+GLOM_B200_API int glom_b200_abi_version(void);
+
+/* Thread-local text of the last error returned on this thread ("" if none). */
+GLOM_B200_API const char* glom_b200_last_error(void);
+
+/* Bytes of the packed-weight buffer for cfg (depends on dim, levels, precision). */
+GLOM_B200_API int glom_b200_packed_weight_bytes(const glom_b200_cfg* cfg, size_t* out_bytes);
+
+/* Repack the reference-layout MLP weights into the engine layout (per level: W1 rows of
+ * bottom-up and top-down interleaved, W2 K-concatenated [bu | td], biases summed where the
+ * combine adds them).  Replaces nothing in the reference: it is the one-time cost of
+ * swapping GroupedFeedForward's Conv1d weights (:29, :31) for GEMM operands. */
+GLOM_B200_API int glom_b200_pack_weights(const glom_b200_cfg* cfg, const glom_b200_weights_ref* w,
+                           void* packed, size_t packed_bytes, void* stream);
+
+/* Workspace bytes glom_b200_forward needs for (cfg, batch, iters, return_all). */
+GLOM_B200_API int glom_b200_workspace_bytes(const glom_b200_cfg* cfg, int batch, int iters,
+                              int return_all, size_t* out_bytes);
+
+/* The hot path: `iters` Jacobi column updates.  Replaces glom_pytorch.py:123-148
+ * (state init/carry, the loop :131-145, hiddens/return_all :147-148).
+ *
+ *   tokens      (B, n, d) fp32   image_to_tokens(img)                     (:114)
+ *   pos         (n, d)    fp32   pos_emb.weight[:n]                       (:117)
+ *   state_in    (B, n, L, d) fp32 contiguous, or NULL                     (:123)
+ *   init_levels (L, d)    fp32   used (broadcast) when state_in == NULL   (:124)
+ *   state_out   return_all ? (iters+1, B, n, L, d) : (B, n, L, d), fp32; slab 0 of the
+ *               return_all form is S_0 (:126).  Must not alias state_in.
+ */
+GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed_weights,
+                      const float* tokens, const float* pos, const float* state_in,
+                      const float* init_levels, float* state_out, int batch, int iters,
+                      int return_all, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tokeniser, the step before the loop: replaces image_to_tokens
+ * (glom_pytorch.py:94-97, call :114): patchify 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
+ * fused with the Linear(3*p*p -> d).
+ *   img (B, 3, H, W) fp32;  weight (d, 3*p*p) fp32;  bias (d) fp32;  tokens (B, n, d) fp32 */
+GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, const float* bias,
+                       float* tokens, int batch, int height, int width, int patch,
+                       int dim, void* stream);
+
+/* Number of kernels the last glom_b200_forward / glom_b200_tokenize call on this thread
+ * enqueued (bench.py reports it as gpu_launches). */
+GLOM_B200_API int glom_b200_last_launch_count(void);
+
+/* Diagnostics: byte offsets of intermediate buffers inside the workspace for the same
+ * (cfg, batch, iters, return_all); tests use them to check single stages.
+ * which: 0 = hidden activations H (rows, (2L-1)*4d), 1 = consensus C (rows, L, d),
+ *        2 = squared-norm partials. Returns GLOM_B200_ERR_INVALID for unknown ids. */
+GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch, int iters, int return_all,
+                               int which, size_t* out_offset, size_t* out_bytes);
+
+/* Per-kernel device timing for the roofline report (bench.py).  Between _begin and _end every
+ * kernel the forward/tokenize calls of THIS thread enqueue is bracketed by CUDA events on the
+ * launch stream (no synchronisation is added to the calls).  _end waits for those events and
+ * returns summed milliseconds and launch counts per kernel kind:
+ *   0 consensus attention, 1 GEMM1+GELU, 2 GEMM2+combine, 3 state prologue, 4 tokeniser.
+ * `kinds` is the capacity of both arrays (>= 5). */
+#define GLOM_B200_PROFILE_KINDS 5
+GLOM_B200_API int glom_b200_profile_begin(void);
+GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kind, int kinds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOM_B200_H_ */

@@ -55,7 +55,7 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
 
 def gelu_erf(x: np.ndarray) -> np.ndarray:
     """nn.GELU() default = 0.5 x (1 + erf(x / sqrt 2))   (glom_pytorch.py:30)."""
-    return (0.5 * x * (1.0 + _erf(x.astype(np.float64) / math.sqrt(2.0)))).astype(x.dtype)
+    return (0.5 * x * (1.0 + _erf(x * x.dtype.type(1.0 / math.sqrt(2.0))))).astype(x.dtype)
 
 
 def synth_params(dim, levels, image_size, patch_size, seed=0, dtype=np.float32):
