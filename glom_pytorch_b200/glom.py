@@ -26,6 +26,13 @@ from torch import nn
 from . import _native
 
 
+def _aligned_bytes(nbytes, device, align=1024):
+    """uint8 device buffer whose data_ptr is `align`-byte aligned (TMA / swizzle-128B bases)."""
+    raw = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + nbytes]
+
+
 class _Patchify(nn.Module):
     """Parameter-free placeholder at index 0 so the Linear keeps the key ``image_to_tokens.1.*``
     (the reference has an einops Rearrange there, glom_pytorch.py:95)."""
@@ -148,7 +155,7 @@ class Glom(nn.Module):
                 t = t.float().contiguous()
             srcs.append(t)
         nbytes = _native.packed_weight_bytes(cfg)
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        packed = _aligned_bytes(nbytes, device)
         _native.pack_weights(cfg, [t.data_ptr() for t in srcs], packed.data_ptr(), nbytes, stream)
         self._packed = (key, packed)
         return packed
@@ -156,7 +163,7 @@ class Glom(nn.Module):
     def _get_workspace(self, nbytes, device):
         ws = self._workspace
         if ws is None or ws.device != device or ws.numel() < nbytes:
-            self._workspace = ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspace = ws = _aligned_bytes(nbytes, device)
         return ws
 
     def engine_cfg(self, n):

@@ -148,12 +148,13 @@ def consensus(levels: np.ndarray, attend_self: bool, mask, emulate=None) -> np.n
     if emulate == "bf16":
         # engine: Gram of the bf16 state, column-scaled by the fp32 reciprocal norm
         qb = bf16_round(q)
-        g = np.einsum("bild,bjld->blij", qb, qb)
+        qt = qb.transpose(0, 2, 1, 3)
+        g = qt @ qt.transpose(0, 1, 3, 2)
         rinv = (1.0 / np.maximum(norm, 1e-12))[..., 0]       # (B, n, L)
         sim = g * rinv.transpose(0, 2, 1)[:, :, None, :] * (d ** -0.5)
         v = qb
     else:
-        sim = np.einsum("bild,bjld->blij", q, k) * (d ** -0.5)   # (:60)
+        sim = (q.transpose(0, 2, 1, 3) @ k.transpose(0, 2, 3, 1)) * (d ** -0.5)   # (:60) 'b i l d, b j l d -> b l i j'
     sim = sim.astype(dt)
     if not attend_self:                                       # (:62-65)
         idx = np.arange(n)
@@ -164,11 +165,11 @@ def consensus(levels: np.ndarray, attend_self: bool, mask, emulate=None) -> np.n
     e = np.exp(sim)
     if emulate == "bf16":
         # engine: unnormalised bf16 probabilities, fp32 row sum of the unrounded ones
-        out = np.einsum("blij,bjld->bild", bf16_round(e), v) / \
+        out = (bf16_round(e) @ v.transpose(0, 2, 1, 3)).transpose(0, 2, 1, 3) / \
             e.sum(-1).transpose(0, 2, 1)[..., None]
         return bf16_round(out.astype(np.float32)).astype(dt)
     attn = e / e.sum(-1, keepdims=True)                       # (:71)
-    return np.einsum("blij,bjld->bild", attn, v).astype(dt)  # (:72)
+    return (attn @ v.transpose(0, 2, 1, 3)).transpose(0, 2, 1, 3).astype(dt)  # (:72) 'b l i j, b j l d -> b i l d'
 
 
 # ----------------------------------------------------------------------------- the path

@@ -232,7 +232,8 @@ def test_permutation_equivariance_over_columns():
         stream = torch.cuda.current_stream().cuda_stream
         packed = m._packed_weights(cfg, x.device, stream)
         out = torch.empty_like(base)
-        ws = torch.empty(_native.workspace_bytes(cfg, 2, 3, False), dtype=torch.uint8, device=DEV)
+        from glom_pytorch_b200.glom import _aligned_bytes
+        ws = _aligned_bytes(_native.workspace_bytes(cfg, 2, 3, False), x.device)
         tp = tok[:, perm].contiguous()
         pp = m.pos_emb.weight.data[perm].contiguous()
         init = m.init_levels.data.contiguous()
