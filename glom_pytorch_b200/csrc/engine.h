@@ -39,7 +39,8 @@ struct Geometry {
   int hidden;      // 4d
   int attend_self, mask_side, mask_d2_max;
   int bn2;         // N tile of the second GEMM: 256 / 128 / 64 (largest dividing d)
-  int nparts;      // squared-norm partials per (row, level) = 2 * d / bn2
+  int part_w;      // columns covered by one squared-norm partial (one epilogue warp group)
+  int nparts;      // squared-norm partials per (row, level) = d / part_w
 };
 
 // ---- packed weights -------------------------------------------------------------------------

@@ -81,7 +81,8 @@ cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const f
 // State prologue of the bf16 path: S_0 -> (fp32 master copy), bf16 shadows, row norms
 // One warp per (row, level).  Replaces glom_pytorch.py:123-126 (+ the casts autocast inserts).
 // =====================================================================================
-__global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, const float* __restrict__ state_in,
+__global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, int part_w,
+                                  const float* __restrict__ state_in,
                                   const float* __restrict__ init_levels, const float* __restrict__ pos,
                                   float* __restrict__ s32_dst, __nv_bfloat16* __restrict__ sb,
                                   __nv_bfloat16* __restrict__ sp, float* __restrict__ nsq) {
@@ -90,10 +91,8 @@ __global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, con
   const int r = warp / L, l = warp % L;
   const float* src = state_in ? state_in + ((size_t)r * L + l) * d : init_levels + (size_t)l * d;
   const float* p = pos + (size_t)(r % n) * d;
-  float ss = 0.f;
   for (int c = lane * 4; c < d; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(src + c);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     const size_t o = ((size_t)r * L + l) * d + c;
     if (s32_dst) *reinterpret_cast<float4*>(s32_dst + o) = v;
     uint2 pk;
@@ -108,9 +107,13 @@ __global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, con
       *reinterpret_cast<uint2*>(sp + ((size_t)r * (L - 1) + (l - 1)) * d + c) = pq;
     }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane < nparts) nsq[((size_t)r * L + l) * nparts + lane] = (lane == 0) ? ss : 0.f;
+  // squared-norm partials in exactly the order the GEMM2 epilogue accumulates them (sequential fmaf
+  // over part_w ascending columns), so a carried-in state continues bit-identically (:123).
+  for (int part = lane; part < nparts; part += 32) {
+    float ss = 0.f;
+    for (int c = 0; c < part_w; ++c) { const float v = src[part * part_w + c]; ss = fmaf(v, v, ss); }
+    nsq[((size_t)r * L + l) * nparts + part] = ss;
+  }
 }
 
 __global__ void cast_bf16_kernel(size_t n4, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
@@ -129,7 +132,7 @@ cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* i
   ProfScope scope(prof, PROF_PREP, st);
   const int warps = g.rows * g.L;
   const int block = 256, grid = (warps * 32 + block - 1) / block;
-  prep_state_kernel<<<grid, block, 0, st>>>(g.rows, g.n, g.L, g.d, g.nparts, state_in, init_levels, pos, s32_dst, sb,
+  prep_state_kernel<<<grid, block, 0, st>>>(g.rows, g.n, g.L, g.d, g.nparts, g.part_w, state_in, init_levels, pos, s32_dst, sb,
                                             sp, nsq);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();

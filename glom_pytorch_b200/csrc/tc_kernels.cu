@@ -8,7 +8,8 @@
 //                       (ConsensusAttention.forward :56-73)
 //
 // All three are warp-specialised: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one
-// lane), warp 2 = TMEM allocator, remaining warps = TMEM->register epilogue / softmax.
+// lane), warp 2 = TMEM allocator, remaining warps = TMEM->register epilogue / softmax.  The GEMMs
+// run on CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA 256 x BN x 16).
 // Operands are staged by TMA into 128B-swizzled shared memory; accumulators live in TMEM.
 #include "engine.h"
 #include "ptx.cuh"
@@ -23,14 +24,15 @@ constexpr int BK = 64;             // bf16 elements per 128-byte swizzle row
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 
 // =====================================================================================
-// K1 / K2: persistent grouped GEMM with fused epilogues
+// K1 / K2: persistent grouped GEMM on CTA pairs (cta_group::2), fused epilogues
+//   cluster of 2 CTAs = one 256 x BN output tile; CTA r owns rows [128 r, 128 r + 128) of it,
+//   loads its 128 rows of A and its half (BN/2 rows) of B; the leader CTA issues UMMA 256xBNx16.
 // =====================================================================================
-constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
-constexpr int GEMM_EPI_THREADS = 256;
+constexpr int GEMM_CTRL_WARPS = 4;
 
 struct GemmParams {
   int rows, d, L, n, G;
-  int num_m, num_n, num_tiles;
+  int num_m, num_n, num_tiles;       // num_m counts 256-row pair tiles
   const float* bias;
   // K1
   __nv_bfloat16* h_out;
@@ -47,11 +49,15 @@ struct GemmParams {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int PARTS = (BN == 256) ? 4 : 2;                 // column parts of a tile = epilogue warp groups
+  static constexpr int PART_COLS = BN / PARTS;                      // 64, 64, 32
+  static constexpr int EPI_WARPS = 4 * PARTS;
+  static constexpr int THREADS = 32 * (GEMM_CTRL_WARPS + EPI_WARPS);
+  static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator stages (power of two >= 32)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator stages
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256;
 };
 
 struct TileInfo {
@@ -73,7 +79,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
 }
 
 template <int MODE, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows, d)        K2: H (rows, G*4d)
             const __grid_constant__ CUtensorMap map_a1,   // K1: state shadow Sb (rows, L*d)
             const __grid_constant__ CUtensorMap map_a2,   // K1: Sb[:,1:]+pos shadow Sp (rows, (L-1)*d)
@@ -81,9 +87,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
             const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPI_THREADS = Cfg::EPI_WARPS * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);    // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -91,6 +99,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -99,20 +111,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();          // peer barriers initialised + both TMEM allocations done before any cross-CTA traffic
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         const TileInfo t = decode_tile<MODE>(p, tile);
         const CUtensorMap* amap;
         int a_col, b_row;
@@ -126,25 +139,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           amap = &map_a0; a_col = 2 * t.z * 4 * p.d;
           b_row = t.z * p.d + t.n_blk * BN;
         }
+        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
+        b_row += (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, amap, &full_bar[stage], a_col + kb * BK, t.m_blk * BM);
-          tma_load_2d(sa + A_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, b_row);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land here
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
+          tma_load_2d_2sm(sa + A_STAGE_BYTES, &map_b, bar, kb * BK, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         const TileInfo t = decode_tile<MODE>(p, tile);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);      // both CTAs' epilogues drained this accumulator stage
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < t.num_kb; ++kb) {
@@ -156,42 +172,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+          umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
+        umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    const int ew = warp - 4;
+  } else if (warp >= GEMM_CTRL_WARPS) {
+    // ------------------------------------------------------------------ epilogue (4 * PARTS warps)
+    const int ew = warp - GEMM_CTRL_WARPS;
+    const int et = threadIdx.x - GEMM_CTRL_WARPS * 32;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                  // column half of the tile
-    constexpr int HALF_COLS = BN / 2;
+    const int part = ew >> 2;                  // column part of the tile
+    constexpr int PART_COLS = Cfg::PART_COLS;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       const TileInfo t = decode_tile<MODE>(p, tile);
+      // stage this tile's bias row in shared memory while the MMAs run
+      {
+        const float* bsrc = (MODE == 0) ? p.bias + (size_t)t.z * 4 * p.d + t.n_blk * BN
+                                        : p.bias + (size_t)t.z * p.d + t.n_blk * BN;
+        for (int i = et; i < BN; i += EPI_THREADS) bias_s[as * BN + i] = __ldg(bsrc + i);
+        named_bar_sync(1, EPI_THREADS);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
-      const int row = t.m_blk * BM + quad * 32 + lane;
+      const int row = t.m_blk * 256 + (int)cta_rank * BM + quad * 32 + lane;
       const bool row_ok = row < p.rows;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * HALF_COLS);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
+      const float* bias = bias_s + as * BN + part * PART_COLS;
       float sumsq = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+      for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
-        const int col = t.n_blk * BN + half * HALF_COLS + c0;    // column inside the group / level
+        const int col = t.n_blk * BN + part * PART_COLS + c0;    // column inside the group / level
         if (MODE == 0) {
-          const float* bias = p.bias + (size_t)t.z * 4 * p.d + col;
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + i));
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + i);
             const float x0 = gelu_erf_fast(__uint_as_float(v[i + 0]) + b4.x);
             const float x1 = gelu_erf_fast(__uint_as_float(v[i + 1]) + b4.y);
             const float x2 = gelu_erf_fast(__uint_as_float(v[i + 2]) + b4.z);
@@ -205,11 +229,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
         } else {
-          if (row_ok && col < p.d) {
+          if (row_ok) {
             const int l = t.z;
             const size_t o = ((size_t)row * p.L + l) * p.d + col;
             const float divisor = (l == p.L - 1) ? 3.0f : 4.0f;                  // (:128-129)
-            const float* bias = p.bias + (size_t)l * p.d + col;
             const float* posr = p.pos + (size_t)(row % p.n) * p.d + col;
             const float4* s4 = reinterpret_cast<const float4*>(p.s32_in + o);
             const uint4* c4 = reinterpret_cast<const uint4*>(p.c_in + o);
@@ -221,8 +244,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
             for (int i = 0; i < 32; i += 8) {
               const float4 sa = s4[i / 4], sb = s4[i / 4 + 1];
               const uint4 cc = c4[i / 8];
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + i));
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+              const float4 ba = *reinterpret_cast<const float4*>(bias + c0 + i);
+              const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i + 4);
               float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
               const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
               const uint32_t cw[4] = {cc.x, cc.y, cc.z, cc.w};
@@ -249,18 +272,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         }
       }
       if (MODE == 1 && row_ok)
-        p.nsq_out[((size_t)row * p.L + t.z) * p.nparts + t.n_blk * 2 + half] = sumsq;
+        p.nsq_out[((size_t)row * p.L + t.z) * p.nparts + t.n_blk * Cfg::PARTS + part] = sumsq;
+      // release this accumulator stage to the leader's MMA issuer: one arrival per epilogue warp of either CTA
       tc_fence_before_sync();
-      mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -577,9 +603,18 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  gemm_kernel<MODE, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, a2, bm, p);
-  return cudaGetLastError();
+  const int max_clusters = num_sms / 2;
+  const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, BN>, a0, a1, a2, bm, p);
 }
 
 int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
@@ -636,10 +671,10 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
     if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
     if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
-    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 256, err, errlen, "W1p")) return -3;
+    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
     GemmParams p{};
     p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + BM - 1) / BM; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
+    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
     p.bias = b.b1; p.h_out = b.h;
     ProfScope scope(prof, PROF_GEMM1, st);
     cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
@@ -649,10 +684,10 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
   // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)
   {
     CUtensorMap mw2;
-    if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2, err, errlen, "W2p")) return -3;
+    if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2 / 2, err, errlen, "W2p")) return -3;
     GemmParams p{};
     p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + BM - 1) / BM; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
+    p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
     p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
     p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
     cudaError_t e;
