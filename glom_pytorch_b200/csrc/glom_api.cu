@@ -85,7 +85,7 @@ static Geometry make_geometry(const glom_b200_cfg* cfg, int batch) {
   g.hidden = 4 * g.d;
   g.attend_self = cfg->attend_self; g.mask_side = cfg->mask_side; g.mask_d2_max = cfg->mask_d2_max;
   g.bn2 = (g.d % 256 == 0) ? 256 : (g.d % 128 == 0) ? 128 : 64;
-  g.part_w = (g.bn2 == 64) ? 32 : 64;     // columns per epilogue warp group (GemmCfg<BN>::PART_COLS)
+  g.part_w = (g.bn2 == 256) ? 64 : g.bn2 / 2;   // columns per GEMM2 epilogue warp group (GemmCfg<1, BN>::PART_COLS)
   g.nparts = g.d / g.part_w;
   return g;
 }

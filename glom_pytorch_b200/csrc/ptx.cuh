@@ -244,4 +244,49 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-a, e, fmaxf(x, 0.0f));
 }
 
+// Packed-pair version for the GEMM1 epilogue (FFMA2 / FADD2: two fp32 lanes per instruction):
+// gelu(acc + bias) for two neighbouring columns, returned as a bf16x2 word.  Uses u = -|x| (one OR per
+// lane instead of abs) and a degree-5 fit of log2(0.5*erfc(a/sqrt2)) on [0,6] whose leading coefficient
+// is negative, so it needs no clamp (p -> -inf, 2^p -> 0 for large |x|); |gelu error| <= 1.9e-6.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t gelu_pair_bf16(float acc0, float acc1, float bias0, float bias1) {
+  const uint64_t x = f2_add(f2_pack(acc0, acc1), f2_pack(bias0, bias1));
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const float u0 = __uint_as_float(__float_as_uint(x0) | 0x80000000u);   // -|x|
+  const float u1 = __uint_as_float(__float_as_uint(x1) | 0x80000000u);
+  const uint64_t u = f2_pack(u0, u1);
+  // p(a) with a = -u: odd coefficients change sign
+  uint64_t q = f2_fma(f2_pack(0.00036467931931838393f, 0.00036467931931838393f), u,
+                      f2_pack(0.006363349035382271f, 0.006363349035382271f));
+  q = f2_fma(q, u, f2_pack(0.05013200640678406f, 0.05013200640678406f));
+  q = f2_fma(q, u, f2_pack(-0.4617065489292145f, -0.4617065489292145f));
+  q = f2_fma(q, u, f2_pack(1.150075078010559f, 1.150075078010559f));
+  q = f2_fma(q, u, f2_pack(-1.0001276731491089f, -1.0001276731491089f));
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  const uint64_t e = f2_pack(ex2_approx(q0), ex2_approx(q1));
+  const uint64_t g = f2_fma(u, e, f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));   // relu(x) - |x| Phi(-|x|)
+  float g0, g1;
+  f2_unpack(g, g0, g1);
+  return pack_bf16x2(g0, g1);
+}
+
 }  // namespace glom

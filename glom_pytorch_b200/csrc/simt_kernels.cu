@@ -107,12 +107,23 @@ __global__ void prep_state_kernel(int rows, int n, int L, int d, int nparts, int
       *reinterpret_cast<uint2*>(sp + ((size_t)r * (L - 1) + (l - 1)) * d + c) = pq;
     }
   }
-  // squared-norm partials in exactly the order the GEMM2 epilogue accumulates them (sequential fmaf
-  // over part_w ascending columns), so a carried-in state continues bit-identically (:123).
-  for (int part = lane; part < nparts; part += 32) {
+  // squared-norm partials in exactly the order the GEMM2 epilogue accumulates them (row_chunk_sumsq in
+  // tc_kernels.cu), so a carried-in state continues bit-identically (:123).
+  // (per 32-column chunk: 8 four-column fmaf chains, pairwise tree; chunks added in order)
+  for (int part = 0; part < nparts; ++part) {
     float ss = 0.f;
-    for (int c = 0; c < part_w; ++c) { const float v = src[part * part_w + c]; ss = fmaf(v, v, ss); }
-    nsq[((size_t)r * L + l) * nparts + part] = ss;
+    for (int c0 = 0; c0 < part_w; c0 += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(src + part * part_w + c0 + (lane & 7) * 4);
+      float q = v.x * v.x;
+      q = fmaf(v.y, v.y, q);
+      q = fmaf(v.z, v.z, q);
+      q = fmaf(v.w, v.w, q);
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      ss += q;
+    }
+    if (lane == 0) nsq[((size_t)r * L + l) * nparts + part] = ss;
   }
 }
 

@@ -15,6 +15,7 @@
 #include "ptx.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace glom {
@@ -27,8 +28,12 @@ constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 // K1 / K2: persistent grouped GEMM on CTA pairs (cta_group::2), fused epilogues
 //   cluster of 2 CTAs = one 256 x BN output tile; CTA r owns rows [128 r, 128 r + 128) of it,
 //   loads its 128 rows of A and its half (BN/2 rows) of B; the leader CTA issues UMMA 256xBNx16.
+//   Epilogue warps read their 32-row TMEM quadrant row-per-thread, then transpose each 32x32 chunk
+//   through a private shared-memory patch so that every global load/store instruction covers whole
+//   cache lines (the reference's 4-way combine / residual write, glom_pytorch.py:141-142).
 // =====================================================================================
 constexpr int GEMM_CTRL_WARPS = 4;
+
 
 struct GemmParams {
   int rows, d, L, n, G;
@@ -47,17 +52,20 @@ struct GemmParams {
   int nparts;
 };
 
-template <int BN>
+template <int MODE, int BN>
 struct GemmCfg {
-  static constexpr int PARTS = (BN == 256) ? 4 : 2;                 // column parts of a tile = epilogue warp groups
-  static constexpr int PART_COLS = BN / PARTS;                      // 64, 64, 32
+  // column parts of a tile = epilogue warp groups: K1 (GELU-heavy) uses 4 parts when the tile allows
+  static constexpr int PARTS = (BN == 256) ? 4 : 2;
+  static constexpr int PART_COLS = BN / PARTS;                      // 64 / 64 / 32
   static constexpr int EPI_WARPS = 4 * PARTS;
   static constexpr int THREADS = 32 * (GEMM_CTRL_WARPS + EPI_WARPS);
   static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? (MODE == 0 ? 6 : 5) : 8;
   static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator stages
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256;
+  static constexpr uint32_t PATCH_BYTES = (MODE == 0) ? 2048 : 4096; // per-warp 32x32 transpose patch (bf16 | f32)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
+                                       (size_t)EPI_WARPS * PATCH_BYTES + BN * 4 /*bias*/ + 256;
 };
 
 struct TileInfo {
@@ -78,50 +86,163 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   return t;
 }
 
+// Sum of squares of a 32-column chunk row, in the canonical order shared with prep_state_kernel:
+// 8 lanes hold 4 consecutive columns each (sequential fmaf), then an xor tree over the 8 lanes.
+__device__ __forceinline__ float row_chunk_sumsq(float a, float b, float c, float d) {
+  float q = a * a;
+  q = fmaf(b, b, q);
+  q = fmaf(c, c, q);
+  q = fmaf(d, d, q);
+  q += __shfl_xor_sync(0xffffffffu, q, 1);
+  q += __shfl_xor_sync(0xffffffffu, q, 2);
+  q += __shfl_xor_sync(0xffffffffu, q, 4);
+  return q;
+}
+
+// ---- K1 epilogue chunk: 32 rows x 32 columns.  Row-per-thread bias + exact-erf GELU + bf16 pack, transpose
+// through the warp's 2 KB patch (16-byte chunk c of row r stored at chunk c ^ ((r >> 1) & 3)), then 64-byte
+// row segments out (8 rows x 64 B per store instruction).
+template <bool FULL>
+__device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch,
+                                         __nv_bfloat16* hdst /* &H[row0][col] */, size_t pitch, int lane, int rows_left) {
+  float4 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = *reinterpret_cast<const float4*>(bias + 4 * i);
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    pk[2 * i] = gelu_pair_bf16(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), b[i].x, b[i].y);
+    pk[2 * i + 1] = gelu_pair_bf16(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b[i].z, b[i].w);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    if (FULL || r < rows_left) *reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8) = val;
+  }
+  __syncwarp();
+}
+
+// ---- K2 epilogue chunk: the 4-way combine (glom_pytorch.py:141-142) on a 32 x 32 accumulator chunk.
+// The accumulators go through the warp's 4 KB patch (f32, 128-byte rows, chunk c of row r at c ^ (r & 7)) so
+// that each lane then owns 4 consecutive columns of 8 rows and every global access covers whole 128-byte lines.
+struct K2Chunk {
+  int l, L, d, n, row0;
+  const float* s32_in; const __nv_bfloat16* c_in; const float* pos;
+  float* s32_out; __nv_bfloat16* sb_out; __nv_bfloat16* sp_out;
+};
+template <bool FULL>
+__device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch, const K2Chunk& k,
+                                         int col, int lane, int rows_left, float (&rowsq)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(patch + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+        make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 7, rsub = lane >> 3;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 4);
+  const bool top = (k.l == k.L - 1);                  // 3 contributions on the top level, 4 elsewhere (:128-129)
+  const bool has_td = (k.l >= 1);
+  const size_t ld = (size_t)k.L * k.d;
+  const size_t base = ((size_t)k.row0 * k.L + k.l) * k.d + col + c * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // global loads of four rows first (independent, all in flight), then combine + store
+    float4 sv[4], pp[4];
+    uint2 cw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (h * 4 + j) * 4 + rsub;
+      sv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pp[j] = sv[j]; cw[j] = make_uint2(0u, 0u);
+      if (FULL || r < rows_left) {
+        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
+        cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld));
+        if (has_td) pp[j] = __ldg(reinterpret_cast<const float4*>(k.pos + (size_t)((k.row0 + r) % k.n) * k.d + col + c * 4));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = h * 4 + j;
+      const int r = i * 4 + rsub;
+      const float4 acc = *reinterpret_cast<const float4*>(patch + r * 128 + ((c ^ (r & 7)) << 4));
+      float o0 = (sv[j].x + (acc.x + b4.x)) + __uint_as_float(cw[j].x << 16);               // (:141)
+      float o1 = (sv[j].y + (acc.y + b4.y)) + __uint_as_float(cw[j].x & 0xFFFF0000u);
+      float o2 = (sv[j].z + (acc.z + b4.z)) + __uint_as_float(cw[j].y << 16);
+      float o3 = (sv[j].w + (acc.w + b4.w)) + __uint_as_float(cw[j].y & 0xFFFF0000u);
+      if (top) { o0 = o0 / 3.0f; o1 = o1 / 3.0f; o2 = o2 / 3.0f; o3 = o3 / 3.0f; }          // (:142) IEEE division
+      else { o0 *= 0.25f; o1 *= 0.25f; o2 *= 0.25f; o3 *= 0.25f; }                          // x/4 == x*0.25 exactly
+      if (FULL || r < rows_left) {
+        const size_t o = base + (size_t)r * ld;
+        __stcs(reinterpret_cast<float4*>(k.s32_out + o), make_float4(o0, o1, o2, o3));
+        *reinterpret_cast<uint2*>(k.sb_out + o) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        if (has_td)
+          *reinterpret_cast<uint2*>(k.sp_out + ((size_t)(k.row0 + r) * (k.L - 1) + (k.l - 1)) * k.d + col + c * 4) =
+              make_uint2(pack_bf16x2(o0 + pp[j].x, o1 + pp[j].y), pack_bf16x2(o2 + pp[j].z, o3 + pp[j].w));
+      } else {
+        o0 = o1 = o2 = o3 = 0.f;
+      }
+      rowsq[i] += row_chunk_sumsq(o0, o1, o2, o3);
+    }
+  }
+  __syncwarp();
+}
+
 template <int MODE, int BN>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<MODE, BN>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows, d)        K2: H (rows, G*4d)
             const __grid_constant__ CUtensorMap map_a1,   // K1: state shadow Sb (rows, L*d)
             const __grid_constant__ CUtensorMap map_a2,   // K1: Sb[:,1:]+pos shadow Sp (rows, (L-1)*d)
             const __grid_constant__ CUtensorMap map_b,    // K1: W1p (G*4d, d)              K2: W2p (L*d, 8d)
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<MODE, BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int EPI_THREADS = Cfg::EPI_WARPS * 32;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);    // [2][BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the shared address space
+  // visible to the compiler: LDS/STS instead of generic LD/ST for every patch / bias / P access)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* patches = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(patches + (size_t)Cfg::EPI_WARPS * Cfg::PATCH_BYTES);    // [BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
+  // Warp roles: epilogue warps come FIRST (ids 0 .. EPI_WARPS-1), the single-lane control warps last: the SM's
+  // warp arbiter favours higher warp ids, and the TMA / MMA issuers must never wait behind epilogue math.
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int W_TMA = Cfg::EPI_WARPS, W_MMA = Cfg::EPI_WARPS + 1, W_ALLOC = Cfg::EPI_WARPS + 2;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
     if (MODE == 0) { tma_prefetch_desc(&map_a1); tma_prefetch_desc(&map_a2); }
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == W_ALLOC) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();          // peer barriers initialised + both TMEM allocations done before any cross-CTA traffic
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -152,7 +273,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
@@ -181,13 +302,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= GEMM_CTRL_WARPS) {
+  } else if (warp < Cfg::EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (4 * PARTS warps)
-    const int ew = warp - GEMM_CTRL_WARPS;
-    const int et = threadIdx.x - GEMM_CTRL_WARPS * 32;
+    const int ew = warp;
+    const int et = threadIdx.x;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int part = ew >> 2;                  // column part of the tile
     constexpr int PART_COLS = Cfg::PART_COLS;
+    uint8_t* patch = patches + (size_t)ew * Cfg::PATCH_BYTES;
     int as = 0; uint32_t aphase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       const TileInfo t = decode_tile<MODE>(p, tile);
@@ -195,84 +317,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       {
         const float* bsrc = (MODE == 0) ? p.bias + (size_t)t.z * 4 * p.d + t.n_blk * BN
                                         : p.bias + (size_t)t.z * p.d + t.n_blk * BN;
-        for (int i = et; i < BN; i += EPI_THREADS) bias_s[as * BN + i] = __ldg(bsrc + i);
+        named_bar_sync(1, EPI_THREADS);          // everyone is done with the previous tile's bias
+        for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
         named_bar_sync(1, EPI_THREADS);
       }
+      const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
+      const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
-      const int row = t.m_blk * 256 + (int)cta_rank * BM + quad * 32 + lane;
-      const bool row_ok = row < p.rows;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
-      const float* bias = bias_s + as * BN + part * PART_COLS;
-      float sumsq = 0.f;
+      const float* bias = bias_s + part * PART_COLS;
+      if (MODE == 0) {
+        __nv_bfloat16* hrow = p.h_out + (size_t)row0 * p.G * 4 * p.d + (size_t)t.z * 4 * p.d + t.n_blk * BN + part * PART_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
-        const int col = t.n_blk * BN + part * PART_COLS + c0;    // column inside the group / level
-        if (MODE == 0) {
-          uint32_t pk[16];
+        for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, 32);
+          else k1_chunk<false>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, rows_left);
+        }
+      } else {
+        K2Chunk kc;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0;
+        kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
+        kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
+        float rowsq[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + i);
-            const float x0 = gelu_erf_fast(__uint_as_float(v[i + 0]) + b4.x);
-            const float x1 = gelu_erf_fast(__uint_as_float(v[i + 1]) + b4.y);
-            const float x2 = gelu_erf_fast(__uint_as_float(v[i + 2]) + b4.z);
-            const float x3 = gelu_erf_fast(__uint_as_float(v[i + 3]) + b4.w);
-            pk[i / 2] = pack_bf16x2(x0, x1);
-            pk[i / 2 + 1] = pack_bf16x2(x2, x3);
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.h_out + (size_t)row * p.G * 4 * p.d + (size_t)t.z * 4 * p.d + col);
+        for (int i = 0; i < 8; ++i) rowsq[i] = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          const int col = t.n_blk * BN + part * PART_COLS + c0;
+          if (rows_left >= 32) k2_chunk<true>(v, bias + c0, patch, kc, col, lane, 32, rowsq);
+          else k2_chunk<false>(v, bias + c0, patch, kc, col, lane, rows_left, rowsq);
+        }
+        if ((lane & 7) == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
-        } else {
-          if (row_ok) {
-            const int l = t.z;
-            const size_t o = ((size_t)row * p.L + l) * p.d + col;
-            const float divisor = (l == p.L - 1) ? 3.0f : 4.0f;                  // (:128-129)
-            const float* posr = p.pos + (size_t)(row % p.n) * p.d + col;
-            const float4* s4 = reinterpret_cast<const float4*>(p.s32_in + o);
-            const uint4* c4 = reinterpret_cast<const uint4*>(p.c_in + o);
-            float4* so4 = reinterpret_cast<float4*>(p.s32_out + o);
-            uint4* sb4 = reinterpret_cast<uint4*>(p.sb_out + o);
-            uint4* sp4 = (l >= 1) ? reinterpret_cast<uint4*>(p.sp_out + ((size_t)row * (p.L - 1) + (l - 1)) * p.d + col)
-                                  : nullptr;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const float4 sa = s4[i / 4], sb = s4[i / 4 + 1];
-              const uint4 cc = c4[i / 8];
-              const float4 ba = *reinterpret_cast<const float4*>(bias + c0 + i);
-              const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i + 4);
-              float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-              const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-              const uint32_t cw[4] = {cc.x, cc.y, cc.z, cc.w};
-              float o8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float cv = __uint_as_float((j & 1) ? (cw[j >> 1] & 0xFFFF0000u) : (cw[j >> 1] << 16));
-                const float mlp = __uint_as_float(v[i + j]) + bv[j];             // BU + TD (+ both second biases)
-                o8[j] = ((sv[j] + mlp) + cv) / divisor;                          // (:141-142)
-                sumsq = fmaf(o8[j], o8[j], sumsq);
-              }
-              so4[i / 4] = make_float4(o8[0], o8[1], o8[2], o8[3]);
-              so4[i / 4 + 1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
-              sb4[i / 8] = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]),
-                                      pack_bf16x2(o8[6], o8[7]));
-              if (sp4) {
-                const float4 pa = __ldg(reinterpret_cast<const float4*>(posr + i));
-                const float4 pb = __ldg(reinterpret_cast<const float4*>(posr + i + 4));
-                sp4[i / 8] = make_uint4(pack_bf16x2(o8[0] + pa.x, o8[1] + pa.y), pack_bf16x2(o8[2] + pa.z, o8[3] + pa.w),
-                                        pack_bf16x2(o8[4] + pb.x, o8[5] + pb.y), pack_bf16x2(o8[6] + pb.z, o8[7] + pb.w));
-              }
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            if (r < rows_left)
+              p.nsq_out[((size_t)(row0 + r) * p.L + t.z) * p.nparts + t.n_blk * Cfg::PARTS + part] = rowsq[i];
           }
         }
       }
-      if (MODE == 1 && row_ok)
-        p.nsq_out[((size_t)row * p.L + t.z) * p.nparts + t.n_blk * Cfg::PARTS + part] = sumsq;
       // release this accumulator stage to the leader's MMA issuer: one arrival per epilogue warp of either CTA
       tc_fence_before_sync();
       __syncwarp();
@@ -284,7 +374,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after_sync();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
@@ -320,7 +410,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
             const __grid_constant__ CUtensorMap map_v,    // box (64, 64, 1)
             const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the shared address space
+  // visible to the compiler: LDS/STS instead of generic LD/ST for every patch / bias / P access)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* p_smem = smem;                                                  // nchunk x [128 x 64] bf16, SW128
   uint8_t* stages = p_smem + (size_t)p.nchunk * A_STAGE_BYTES;
   float* rs = reinterpret_cast<float*>(stages + (size_t)p.num_stages * ATTN_STAGE_BYTES);   // [n_pad16]
@@ -331,25 +423,27 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   uint64_t* pready_bar = aempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pready_bar + 1);
 
+  // softmax / output warps are warps 0-3, control warps 4-6 (higher ids win the warp arbiter)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4, W_MMA = 5, W_ALLOC = 6;
   const int q0 = blockIdx.x * BM, l = blockIdx.y, b = blockIdx.z;
   const int npass = (p.d + 255) / 256;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
-  if (warp == 1 && lane == 0) {
+  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], ATTN_SM_THREADS); }
     mbar_init(pready_bar, ATTN_SM_THREADS);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == W_ALLOC) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < p.nkb; ++kb) {
@@ -374,7 +468,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int job = 0;
@@ -425,12 +519,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         umma_commit(&afull_bar[buf]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------ softmax + output warps
     const int quad = warp & 3;
     const int t = quad * 32 + lane;          // query row inside the tile == TMEM lane
     const int qi = q0 + t;
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x;
     const size_t img_row0 = (size_t)b * p.n;
     constexpr float LOG2E = 1.4426950408889634f;
     const float NEG_INF = __int_as_float(0xff800000);
@@ -559,7 +653,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
@@ -595,7 +689,7 @@ static bool map2d(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t 
 template <int MODE, int BN>
 static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
                                const GemmParams& p, int num_sms, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<MODE, BN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
