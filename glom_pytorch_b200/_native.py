@@ -13,7 +13,7 @@ PRECISION = {"fp32": 0, "bf16": 1}
 EXPORTS = (
     "glom_b200_abi_version", "glom_b200_last_error", "glom_b200_packed_weight_bytes",
     "glom_b200_pack_weights", "glom_b200_workspace_bytes", "glom_b200_forward",
-    "glom_b200_tokenize", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
+    "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
 )
 PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize")
@@ -57,7 +57,9 @@ def load():
     lib.glom_b200_workspace_offset.argtypes = [ctypes.POINTER(Cfg), i32, i32, i32, i32,
                                                ctypes.POINTER(sz), ctypes.POINTER(sz)]
     lib.glom_b200_forward.argtypes = [ctypes.POINTER(Cfg), vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
-    lib.glom_b200_tokenize.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.glom_b200_tokenize.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.glom_b200_tokenize_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
+    lib.glom_b200_tokenize_workspace_bytes.restype = i32
     lib.glom_b200_profile_begin.restype = i32
     lib.glom_b200_profile_end.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
     lib.glom_b200_profile_end.restype = i32
@@ -110,8 +112,16 @@ def forward(cfg, packed_ptr, tokens_ptr, pos_ptr, state_in_ptr, init_ptr, out_pt
                                    out_ptr, batch, iters, int(return_all), ws_ptr, ws_bytes, stream))
 
 
-def tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim, stream):
-    check(load().glom_b200_tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim, stream))
+def tokenize_workspace_bytes(batch, height, width, patch, dim, precision):
+    out = ctypes.c_size_t()
+    check(load().glom_b200_tokenize_workspace_bytes(batch, height, width, patch, dim, PRECISION[precision],
+                                                    ctypes.byref(out)))
+    return out.value
+
+
+def tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim, precision, ws_ptr, ws_bytes, stream):
+    check(load().glom_b200_tokenize(img_ptr, w_ptr, b_ptr, out_ptr, batch, height, width, patch, dim,
+                                    PRECISION[precision], ws_ptr, ws_bytes, stream))
 
 
 def last_launch_count():

@@ -110,6 +110,12 @@ cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const f
 cudaError_t launch_tokenize(const float* img, const float* w, const float* bias, float* tokens, int B, int H, int W,
                             int p, int d, cudaStream_t st, int* launches, Profiler* prof);
 
+// bf16 tokeniser: patchify + cast (CUDA cores), then the tcgen05 GEMM
+cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16* patches, __nv_bfloat16* wtok, int B,
+                                 int H, int W, int p, int d, int kp, cudaStream_t st, int* launches);
+int tokenize_tc(const __nv_bfloat16* patches, const __nv_bfloat16* wtok, const float* bias, float* tokens, int rows,
+                int d, int kp, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace glom

@@ -259,17 +259,51 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
   return 0;
 }
 
+static int tok_kp(int patch) { return (3 * patch * patch + 63) / 64 * 64; }
+
+GLOM_B200_API int glom_b200_tokenize_workspace_bytes(int batch, int height, int width, int patch, int dim, int precision,
+                                                     size_t* out_bytes) {
+  if (!out_bytes || batch < 1 || patch < 1 || dim < 1 || height < patch || width < patch || height % patch || width % patch)
+    return fail(GLOM_B200_ERR_INVALID, "bad tokeniser geometry");
+  if (precision == GLOM_B200_BF16) {
+    const size_t rows = (size_t)batch * (height / patch) * (width / patch);
+    *out_bytes = align_up(rows * tok_kp(patch) * 2, 1024) + align_up((size_t)dim * tok_kp(patch) * 2, 1024);
+  } else {
+    *out_bytes = 0;
+  }
+  return 0;
+}
+
 GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, const float* bias, float* tokens, int batch, int height,
-                       int width, int patch, int dim, void* stream) {
+                       int width, int patch, int dim, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (!img || !weight || !bias || !tokens) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
   if (batch < 1 || patch < 1 || dim < 1 || height < patch || width < patch || height % patch || width % patch)
     return fail(GLOM_B200_ERR_INVALID, "image %dx%d is not a positive multiple of patch %d", height, width, patch);
+  if (precision != GLOM_B200_FP32 && precision != GLOM_B200_BF16) return fail(GLOM_B200_ERR_INVALID, "unknown precision %d", precision);
   DeviceInfo di{};
   if (int r = device_info(&di)) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   g_launches = 0;
-  cudaError_t e = launch_tokenize(img, weight, bias, tokens, batch, height, width, patch, dim,
-                                  static_cast<cudaStream_t>(stream), &g_launches, &g_prof);
-  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "tokenize launch: %s", cudaGetErrorString(e));
+  if (precision == GLOM_B200_FP32) {
+    cudaError_t e = launch_tokenize(img, weight, bias, tokens, batch, height, width, patch, dim, st, &g_launches, &g_prof);
+    if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "tokenize launch: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (dim % 64) return fail(GLOM_B200_ERR_INVALID, "bf16 tokeniser needs dim %% 64 == 0 (got %d)", dim);
+  size_t need = 0;
+  glom_b200_tokenize_workspace_bytes(batch, height, width, patch, dim, precision, &need);
+  if (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 1024)
+    return fail(GLOM_B200_ERR_WORKSPACE, "tokeniser workspace: need %zu bytes 1024-aligned, got %zu", need, workspace_bytes);
+  const int kp = tok_kp(patch);
+  const int rows = batch * (height / patch) * (width / patch);
+  __nv_bfloat16* patches = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* wtok = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(workspace) + align_up((size_t)rows * kp * 2, 1024));
+  ProfScope scope(&g_prof, PROF_TOKENIZE, st);
+  cudaError_t e = launch_patchify_bf16(img, weight, patches, wtok, batch, height, width, patch, dim, kp, st, &g_launches);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "patchify launch: %s", cudaGetErrorString(e));
+  char msg[300] = "";
+  if (int r = tokenize_tc(patches, wtok, bias, tokens, rows, dim, kp, g_encode, di.sms, st, &g_launches, msg, sizeof(msg)))
+    return fail(GLOM_B200_ERR_CUDA, "%s", msg);
   return 0;
 }
 

@@ -410,4 +410,52 @@ cudaError_t launch_tokenize(const float* img, const float* w, const float* bias,
   return cudaGetLastError();
 }
 
+
+// =====================================================================================
+// bf16 tokeniser front end: 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (glom_pytorch.py:95) gathered straight into
+// the zero-padded bf16 A operand (rows, kp) of the tensor-core GEMM, and the Linear weight cast to (d, kp) bf16.
+// =====================================================================================
+__global__ void patchify_bf16_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                     __nv_bfloat16* __restrict__ patches, __nv_bfloat16* __restrict__ wtok, int B, int H,
+                                     int W, int p, int d, int kp) {
+  const int hp = H / p, wp = W / p, k3 = 3 * p * p;
+  const size_t rows = (size_t)B * hp * wp;
+  const size_t n_pairs = rows * (kp / 2), w_pairs = (size_t)d * (kp / 2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs + w_pairs;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float v[2];
+    if (i < n_pairs) {
+      const size_t r = i / (kp / 2);
+      const int k0 = (int)(i % (kp / 2)) * 2;
+      const int b = (int)(r / ((size_t)hp * wp)), pr = (int)(r % ((size_t)hp * wp)), ph = pr / wp, pw = pr % wp;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = k0 + e;
+        v[e] = 0.f;
+        if (k < k3) {
+          const int c = k % 3, p12 = k / 3, p1 = p12 / p, p2 = p12 % p;
+          v[e] = img[(((size_t)b * 3 + c) * H + ph * p + p1) * W + pw * p + p2];
+        }
+      }
+      reinterpret_cast<uint32_t*>(patches)[i] = pack_bf16x2(v[0], v[1]);
+    } else {
+      const size_t q = i - n_pairs;
+      const size_t row = q / (kp / 2);
+      const int k0 = (int)(q % (kp / 2)) * 2;
+      v[0] = (k0 < k3) ? w[row * k3 + k0] : 0.f;
+      v[1] = (k0 + 1 < k3) ? w[row * k3 + k0 + 1] : 0.f;
+      reinterpret_cast<uint32_t*>(wtok)[q] = pack_bf16x2(v[0], v[1]);
+    }
+  }
+}
+
+cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16* patches, __nv_bfloat16* wtok, int B,
+                                 int H, int W, int p, int d, int kp, cudaStream_t st, int* launches) {
+  const size_t total = ((size_t)B * (H / p) * (W / p) + d) * (kp / 2);
+  const size_t want = (total + 255) / 256;
+  patchify_bf16_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(img, w, patches, wtok, B, H, W, p, d, kp);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 }  // namespace glom

@@ -50,6 +50,10 @@ struct GemmParams {
   __nv_bfloat16* sp_out;
   float* nsq_out;
   int nparts;
+  int probe;
+  // tokeniser (MODE 2)
+  float* tok_out;
+  int tok_kb;      // K blocks of 64 of the zero-padded patch dimension
 };
 
 template <int MODE, int BN>
@@ -61,9 +65,10 @@ struct GemmCfg {
   static constexpr int THREADS = 32 * (GEMM_CTRL_WARPS + EPI_WARPS);
   static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? (MODE == 0 ? 6 : 5) : 8;
+  static constexpr int STAGES = (BN == 256) ? (MODE == 0 ? 6 : 5) : 8;   // 32 KB stages + patches must fit 227 KB
   static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator stages
   static constexpr uint32_t PATCH_BYTES = (MODE == 0) ? 2048 : 4096; // per-warp 32x32 transpose patch (bf16 | f32)
+  static_assert(MODE >= 0 && MODE <= 2, "0 = GEMM1+GELU, 1 = GEMM2+combine, 2 = tokeniser");
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
                                        (size_t)EPI_WARPS * PATCH_BYTES + BN * 4 /*bias*/ + 256;
 };
@@ -82,7 +87,8 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   t.m_blk = r % p.num_m;
   t.z = r / p.num_m;
   if (MODE == 0) t.num_kb = p.d / BK;
-  else t.num_kb = ((t.z == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;   // top level: no top-down half (:137)
+  else if (MODE == 1) t.num_kb = ((t.z == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;   // top level: no top-down half (:137)
+  else t.num_kb = p.tok_kb;
   return t;
 }
 
@@ -129,11 +135,32 @@ __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* b
   __syncwarp();
 }
 
+// ---- tokeniser epilogue chunk (image_to_tokens Linear bias, glom_pytorch.py:96): f32 out, whole 128-byte lines.
+__device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch, float* dst,
+                                          size_t pitch, int lane, int rows_left) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(patch + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+        make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int c = lane & 7, rsub = lane >> 3;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const float4 a = *reinterpret_cast<const float4*>(patch + r * 128 + ((c ^ (r & 7)) << 4));
+    if (r < rows_left)
+      *reinterpret_cast<float4*>(dst + (size_t)r * pitch + c * 4) = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+  }
+  __syncwarp();
+}
+
 // ---- K2 epilogue chunk: the 4-way combine (glom_pytorch.py:141-142) on a 32 x 32 accumulator chunk.
 // The accumulators go through the warp's 4 KB patch (f32, 128-byte rows, chunk c of row r at c ^ (r & 7)) so
 // that each lane then owns 4 consecutive columns of 8 rows and every global access covers whole 128-byte lines.
 struct K2Chunk {
   int l, L, d, n, row0;
+  int probe;   // development probe (GLOM_B200_PROBE): 1 = all rows load the same lines, 2 = all rows store to the same lines
   const float* s32_in; const __nv_bfloat16* c_in; const float* pos;
   float* s32_out; __nv_bfloat16* sb_out; __nv_bfloat16* sp_out;
 };
@@ -150,6 +177,7 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
   const bool top = (k.l == k.L - 1);                  // 3 contributions on the top level, 4 elsewhere (:128-129)
   const bool has_td = (k.l >= 1);
   const size_t ld = (size_t)k.L * k.d;
+  const size_t ld_in = (k.probe & 1) ? 0 : ld, ld_out = (k.probe & 2) ? 0 : ld;
   const size_t base = ((size_t)k.row0 * k.L + k.l) * k.d + col + c * 4;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -161,8 +189,8 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
       const int r = (h * 4 + j) * 4 + rsub;
       sv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pp[j] = sv[j]; cw[j] = make_uint2(0u, 0u);
       if (FULL || r < rows_left) {
-        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
-        cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld));
+        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld_in));
+        cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld_in));
         if (has_td) pp[j] = __ldg(reinterpret_cast<const float4*>(k.pos + (size_t)((k.row0 + r) % k.n) * k.d + col + c * 4));
       }
     }
@@ -178,11 +206,11 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
       if (top) { o0 = o0 / 3.0f; o1 = o1 / 3.0f; o2 = o2 / 3.0f; o3 = o3 / 3.0f; }          // (:142) IEEE division
       else { o0 *= 0.25f; o1 *= 0.25f; o2 *= 0.25f; o3 *= 0.25f; }                          // x/4 == x*0.25 exactly
       if (FULL || r < rows_left) {
-        const size_t o = base + (size_t)r * ld;
+        const size_t o = base + (size_t)r * ld_out;
         __stcs(reinterpret_cast<float4*>(k.s32_out + o), make_float4(o0, o1, o2, o3));
         *reinterpret_cast<uint2*>(k.sb_out + o) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         if (has_td)
-          *reinterpret_cast<uint2*>(k.sp_out + ((size_t)(k.row0 + r) * (k.L - 1) + (k.l - 1)) * k.d + col + c * 4) =
+          *reinterpret_cast<uint2*>(k.sp_out + ((size_t)(k.row0 + ((k.probe & 2) ? 0 : r)) * (k.L - 1) + (k.l - 1)) * k.d + col + c * 4) =
               make_uint2(pack_bf16x2(o0 + pp[j].x, o1 + pp[j].y), pack_bf16x2(o2 + pp[j].z, o3 + pp[j].w));
       } else {
         o0 = o1 = o2 = o3 = 0.f;
@@ -256,11 +284,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           else if (t.z & 1) { amap = &map_a2; a_col = l * p.d; }              // top-down l reads S[l+1]+pos (:136)
           else { amap = &map_a1; a_col = (l - 1) * p.d; }                     // bottom-up l reads S[l-1]   (:134)
           b_row = t.z * 4 * p.d + t.n_blk * BN;
-        } else {
+        } else if (MODE == 1) {
           amap = &map_a0; a_col = 2 * t.z * 4 * p.d;
           b_row = t.z * p.d + t.n_blk * BN;
+        } else {
+          amap = &map_a0; a_col = 0;               // patches (rows, Kp) x Wtok (d, Kp)
+          b_row = t.n_blk * BN;
         }
-        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
+        const int a_row = ((p.probe & 8) ? 0 : t.m_blk * 256) + (int)cta_rank * BM;
         b_row += (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -316,7 +347,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       // stage this tile's bias row in shared memory while the MMAs run
       {
         const float* bsrc = (MODE == 0) ? p.bias + (size_t)t.z * 4 * p.d + t.n_blk * BN
-                                        : p.bias + (size_t)t.z * p.d + t.n_blk * BN;
+                                        : p.bias + (size_t)t.z * p.d + t.n_blk * BN;   // MODE 2: z == 0
         named_bar_sync(1, EPI_THREADS);          // everyone is done with the previous tile's bias
         for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
         named_bar_sync(1, EPI_THREADS);
@@ -337,9 +368,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, 32);
           else k1_chunk<false>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, rows_left);
         }
+      } else if (MODE == 2) {
+        float* trow = p.tok_out + (size_t)row0 * p.d + t.n_blk * BN + part * PART_COLS;
+#pragma unroll 1
+        for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          tok_chunk(v, bias + c0, patch, trow + c0, (size_t)p.d, lane, rows_left);
+        }
       } else {
         K2Chunk kc;
-        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = (p.probe & 4) ? 0 : row0; kc.probe = p.probe;
         kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
         kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
         float rowsq[8];
@@ -387,8 +427,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
 //   phase 2: O = P V per 256-wide slice of d (V read MN-major straight from the state shadow),
 //            scaled by 1/rowsum and written as bf16 C.
 // =====================================================================================
-constexpr int ATTN_THREADS = 256;
-constexpr int ATTN_SM_THREADS = 128;
+constexpr int ATTN_SM_WARPS = 8;                  // softmax / output warps: 4 TMEM quadrants x 2 column halves
+constexpr int ATTN_THREADS = 384;                 // 8 softmax warps + TMA + MMA + TMEM-alloc + 1 idle
+constexpr int ATTN_SM_THREADS = ATTN_SM_WARPS * 32;
 constexpr int ATTN_MAX_KB = 4;
 constexpr uint32_t ATTN_STAGE_BYTES = A_STAGE_BYTES + 256 * 128;   // Q tile + K block (or V slice)
 
@@ -416,17 +457,18 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   uint8_t* p_smem = smem;                                                  // nchunk x [128 x 64] bf16, SW128
   uint8_t* stages = p_smem + (size_t)p.nchunk * A_STAGE_BYTES;
   float* rs = reinterpret_cast<float*>(stages + (size_t)p.num_stages * ATTN_STAGE_BYTES);   // [n_pad16]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rs + p.n_pad16);
+  float* red = rs + p.n_pad16;                                              // [768]: block max x2 parities, row sums
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 768);
   uint64_t* empty_bar = full_bar + p.num_stages;
   uint64_t* afull_bar = empty_bar + p.num_stages;
   uint64_t* aempty_bar = afull_bar + 2;
   uint64_t* pready_bar = aempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pready_bar + 1);
 
-  // softmax / output warps are warps 0-3, control warps 4-6 (higher ids win the warp arbiter)
+  // softmax / output warps are warps 0-7, control warps 8-10 (higher ids win the warp arbiter)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int W_TMA = 4, W_MMA = 5, W_ALLOC = 6;
+  constexpr int W_TMA = ATTN_SM_WARPS, W_MMA = ATTN_SM_WARPS + 1, W_ALLOC = ATTN_SM_WARPS + 2;
   const int q0 = blockIdx.x * BM, l = blockIdx.y, b = blockIdx.z;
   const int npass = (p.d + 255) / 256;
 
@@ -519,9 +561,11 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         umma_commit(&afull_bar[buf]);
       }
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------------ softmax + output warps
-    const int quad = warp & 3;
+  } else if (warp < ATTN_SM_WARPS) {
+    // ------------------------------------------------------------------ softmax + output warps (8)
+    // warp = (quad, half): TMEM lane quadrant `quad` (32 query rows, one per thread) x column half `half`
+    // of every key block / output slice; row maxima and sums are combined across the two halves in smem.
+    const int quad = warp & 3, half = warp >> 2;
     const int t = quad * 32 + lane;          // query row inside the tile == TMEM lane
     const int qi = q0 + t;
     const int tid = threadIdx.x;
@@ -542,39 +586,46 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
     }
     named_bar_sync(1, ATTN_SM_THREADS);
 
-    const int qh = (p.mask_side > 0) ? qi / p.mask_side : 0, qw = (p.mask_side > 0) ? qi % p.mask_side : 0;
+    const bool use_mask = p.mask_side > 0;
+    const int qh = use_mask ? qi / p.mask_side : 0, qw = use_mask ? qi % p.mask_side : 0;
+    const int diag = p.attend_self ? -1 : qi;
     auto logit = [&](uint32_t raw, int j) -> float {
       float sv = __uint_as_float(raw) * rs[j];                                      // (:60)
-      if (!p.attend_self && j == qi) sv = -5e-4f;                                   // (:62-65)
+      sv = (j == diag) ? -5e-4f : sv;                                               // (:62-65)
       bool masked = j >= p.n;
-      if (p.mask_side > 0) {                                                        // (:67-69)
+      if (use_mask) {                                                               // (:67-69)
         const int dh = qh - j / p.mask_side, dw = qw - j % p.mask_side;
         masked |= (dh * dh + dw * dw > p.mask_d2_max);
       }
       return masked ? NEG_INF : sv;
     };
 
-    float m_run = NEG_INF, l_run = 0.f;
+    float m_run = NEG_INF, l_run = 0.f;      // l_run: this warp's column half only
     float m_used[ATTN_MAX_KB];
     int job = 0;
     for (int kb = 0; kb < p.nkb; ++kb, ++job) {
       const int w = min(256, p.n_pad16 - kb * 256);
+      const int wlo = ((w >> 5) + ((w >> 4) & 1)) << 4;      // columns of half 0 (multiple of 16, >= w/2)
+      const int cbeg = half ? wlo : 0, cend = half ? w : wlo;
       const int buf = job & 1;
       mbar_wait(&afull_bar[buf], (job >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
       float bm = NEG_INF;
-      for (int c0 = 0; c0 < w; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) bm = fmaxf(bm, logit(v[i], kb * 256 + c0 + i));
       }
+      red[(kb & 1) * 256 + half * 128 + t] = bm;                     // exchange the block max with the other half
+      named_bar_sync(2 + quad, 64);
+      bm = fmaxf(bm, red[(kb & 1) * 256 + (half ^ 1) * 128 + t]);
       const float m_new = fmaxf(m_run, bm);
       const float m_safe = (m_new == NEG_INF) ? 0.f : m_new;
       l_run *= (m_run == NEG_INF) ? 0.f : ex2_approx((m_run - m_safe) * LOG2E);
-      for (int c0 = 0; c0 < w; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c0, v);
         tmem_ld_wait();
@@ -603,7 +654,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       if (m_used[kb] == m_fin) continue;
       const float f = ex2_approx((m_used[kb] - m_fin) * LOG2E);
       const int w = min(256, p.n_pad16 - kb * 256);
-      for (int c0 = 0; c0 < w; c0 += 8) {
+      const int wlo = ((w >> 5) + ((w >> 4) & 1)) << 4;
+      const int cbeg = half ? wlo : 0, cend = half ? w : wlo;
+      for (int c0 = cbeg; c0 < cend; c0 += 8) {
         const int key = kb * 256 + c0;
         uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
                                               ((((key & 63) >> 3) ^ (t & 7)) << 4));
@@ -617,34 +670,52 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         *ptr = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       }
     }
-    for (int key = p.n_pad16; key < p.n_pad64; key += 8) {
-      uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
-                                            ((((key & 63) >> 3) ^ (t & 7)) << 4));
-      *ptr = make_uint4(0, 0, 0, 0);
+    if (half == 1) {
+      for (int key = p.n_pad16; key < p.n_pad64; key += 8) {
+        uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
+                                              ((((key & 63) >> 3) ^ (t & 7)) << 4));
+        *ptr = make_uint4(0, 0, 0, 0);
+      }
     }
+    red[512 + half * 128 + t] = l_run;                                 // row sum = sum of both halves
     fence_proxy_async_smem();
     mbar_arrive(pready_bar);
+    named_bar_sync(2 + quad, 64);
+    const float inv_l = 1.0f / (l_run + red[512 + (half ^ 1) * 128 + t]);
 
-    const float inv_l = 1.0f / l_run;
+    // output: O slice (128 x <=256) from TMEM, scaled by 1/rowsum, bf16, transposed through a 2 KB patch
+    // (in the Q area of pipeline stage 0, idle in phase 2) so that stores cover 64-byte row segments
+    uint8_t* patch = stages + (size_t)warp * 2048;
+    const int rows_left = p.n - (q0 + quad * 32);
     for (int ps = 0; ps < npass; ++ps, ++job) {
       const int wd = min(256, p.d - ps * 256);
+      const int hw = ((wd >> 6) + ((wd >> 5) & 1)) << 5;              // columns of half 0 (multiple of 32)
+      const int cbeg = half ? hw : 0, cend = half ? wd : hw;
       const int buf = job & 1;
       mbar_wait(&afull_bar[buf], (job >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-      for (int c0 = 0; c0 < wd; c0 += 32) {
+      __nv_bfloat16* cdst = p.c_out + ((img_row0 + q0 + quad * 32) * p.L + l) * p.d + ps * 256;
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
-        if (qi < p.n) {
-          uint4* dst = reinterpret_cast<uint4*>(p.c_out + ((img_row0 + qi) * p.L + l) * p.d + ps * 256 + c0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l),
-                                pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l),
-                                pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l),
-                                pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l));
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(
+              pack_bf16x2(__uint_as_float(v[8 * c + 0]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
+              pack_bf16x2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
+              pack_bf16x2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
+              pack_bf16x2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
+        __syncwarp();
+        const int c = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2);
+          const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+          if (r < rows_left) *reinterpret_cast<uint4*>(cdst + (size_t)r * p.L * p.d + c0 + c * 8) = val;
         }
+        __syncwarp();
       }
       tc_fence_before_sync();
       mbar_arrive(&aempty_bar[buf]);
@@ -714,7 +785,25 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
 int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
               char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
-  // ---------------- K3: consensus attention -> C
+  // ---------------- K1: grouped GEMM1 + bias + GELU -> H
+  CUtensorMap mh;
+  if (!map2d(enc, &mh, b.h, rows, (uint64_t)g.G * 4 * d, BM, err, errlen, "H")) return -3;
+  {
+    CUtensorMap mx, msb, msp, mw1;
+    if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
+    if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
+    if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
+    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
+    GemmParams p{};
+    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
+    p.bias = b.b1; p.h_out = b.h;
+    ProfScope scope(prof, PROF_GEMM1, st);
+    cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
+  }
+  // ---------------- K3: consensus attention -> C  (after K1 so that C is still L2-resident when K2's combine reads it)
   {
     AttnParams ap{};
     ap.n = n; ap.L = L; ap.d = d;
@@ -729,7 +818,7 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     ap.c_out = b.c;
     ap.scale = 1.0f / sqrtf((float)d);
     if (ap.nkb > ATTN_MAX_KB) { snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n); return -1; }
-    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + (size_t)ap.n_pad16 * 4 + 256;
+    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + (size_t)ap.n_pad16 * 4 + 768 * 4 + 256;
     const size_t max_smem = 227 * 1024;
     int stages = 4;
     while (stages > 0 && fixed + (size_t)stages * ATTN_STAGE_BYTES > max_smem) --stages;
@@ -757,24 +846,6 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
   }
-  // ---------------- K1: grouped GEMM1 + bias + GELU -> H
-  CUtensorMap mh;
-  if (!map2d(enc, &mh, b.h, rows, (uint64_t)g.G * 4 * d, BM, err, errlen, "H")) return -3;
-  {
-    CUtensorMap mx, msb, msp, mw1;
-    if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
-    if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
-    if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
-    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
-    GemmParams p{};
-    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
-    p.bias = b.b1; p.h_out = b.h;
-    ProfScope scope(prof, PROF_GEMM1, st);
-    cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
-    if (launches) ++*launches;
-    if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
-  }
   // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)
   {
     CUtensorMap mw2;
@@ -784,6 +855,7 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
     p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
     p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+    { const char* pv = getenv("GLOM_B200_PROBE"); p.probe = pv ? atoi(pv) : 0; }
     cudaError_t e;
     ProfScope scope(prof, PROF_GEMM2, st);
     if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
@@ -792,6 +864,27 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     if (launches) ++*launches;
     if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
   }
+  return 0;
+}
+
+
+// ---------------- tensor-core tokeniser: tokens = patches(bf16) . Wtok(bf16)^T + bias   (glom_pytorch.py:94-97)
+int tokenize_tc(const __nv_bfloat16* patches, const __nv_bfloat16* wtok, const float* bias, float* tokens, int rows,
+                int d, int kp, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen) {
+  const int bn = (d % 256 == 0) ? 256 : (d % 128 == 0) ? 128 : 64;
+  CUtensorMap ma, mb;
+  if (!map2d(enc, &ma, patches, rows, kp, BM, err, errlen, "patches")) return -3;
+  if (!map2d(enc, &mb, wtok, d, kp, (uint32_t)bn / 2, err, errlen, "Wtok")) return -3;
+  GemmParams p{};
+  p.rows = rows; p.d = d; p.L = 1; p.n = 1; p.G = 1;
+  p.num_m = (rows + 255) / 256; p.num_n = d / bn; p.num_tiles = p.num_m * p.num_n;
+  p.bias = bias; p.tok_out = tokens; p.tok_kb = kp / BK;
+  cudaError_t e;
+  if (bn == 256) e = launch_gemm<2, 256>(ma, ma, ma, mb, p, num_sms, st);
+  else if (bn == 128) e = launch_gemm<2, 128>(ma, ma, ma, mb, p, num_sms, st);
+  else e = launch_gemm<2, 64>(ma, ma, ma, mb, p, num_sms, st);
+  if (launches) ++*launches;
+  if (e != cudaSuccess) { snprintf(err, errlen, "tokeniser gemm launch: %s", cudaGetErrorString(e)); return -3; }
   return 0;
 }
 

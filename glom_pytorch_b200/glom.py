@@ -171,7 +171,7 @@ class Glom(nn.Module):
         return _native.make_cfg(self.dim, self.levels, n, self.attention.attend_self, side, d2, self.precision)
 
     def tokens(self, img):
-        """image_to_tokens (:114) -- the engine's fused patchify+Linear kernel, fp32."""
+        """image_to_tokens (:114): fp32 CUDA-core kernel (precision fp32) or bf16 gather + tcgen05 GEMM (bf16)."""
         lin = self.image_to_tokens[1]
         b, c, h, w = img.shape
         p = self.patch_size
@@ -182,7 +182,12 @@ class Glom(nn.Module):
         img = img.float().contiguous()
         out = torch.empty(b, (h // p) * (w // p), self.dim, dtype=torch.float32, device=img.device)
         wt, bs = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+        tws_bytes = _native.tokenize_workspace_bytes(b, h, w, p, self.dim, self.precision)
+        tws = getattr(self, "_tok_ws", None)
+        if tws_bytes and (tws is None or tws.device != img.device or tws.numel() < tws_bytes):
+            self._tok_ws = tws = _aligned_bytes(tws_bytes, img.device)
         _native.tokenize(img.data_ptr(), wt.data_ptr(), bs.data_ptr(), out.data_ptr(), b, h, w, p, self.dim,
+                         self.precision, tws.data_ptr() if tws_bytes else None, tws_bytes,
                          torch.cuda.current_stream(img.device).cuda_stream)
         self._tok_launches = _native.last_launch_count()
         return out

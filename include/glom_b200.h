@@ -109,10 +109,15 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
 /* Tokeniser, the step before the loop: replaces image_to_tokens
  * (glom_pytorch.py:94-97, call :114): patchify 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
  * fused with the Linear(3*p*p -> d).
- *   img (B, 3, H, W) fp32;  weight (d, 3*p*p) fp32;  bias (d) fp32;  tokens (B, n, d) fp32 */
+ *   img (B, 3, H, W) fp32;  weight (d, 3*p*p) fp32;  bias (d) fp32;  tokens (B, n, d) fp32
+ * precision GLOM_B200_FP32: one CUDA-core fp32 kernel, no workspace.
+ * precision GLOM_B200_BF16: gather + cast to a zero-padded bf16 operand, then a tcgen05 GEMM with
+ *   fp32 accumulation (what autocast does to this Linear); needs the workspace below, 1024-aligned. */
+GLOM_B200_API int glom_b200_tokenize_workspace_bytes(int batch, int height, int width, int patch,
+                                                     int dim, int precision, size_t* out_bytes);
 GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, const float* bias,
                        float* tokens, int batch, int height, int width, int patch,
-                       int dim, void* stream);
+                       int dim, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels the last glom_b200_forward / glom_b200_tokenize call on this thread
  * enqueued (bench.py reports it as gpu_launches). */

@@ -93,14 +93,17 @@ def synth_params(dim, levels, image_size, patch_size, seed=0, dtype=np.float32):
 
 
 # ----------------------------------------------------------------------------- operators
-def tokenize(img: np.ndarray, w: np.ndarray, b: np.ndarray, patch_size: int) -> np.ndarray:
-    """image_to_tokens (:94-97, call :114). img (B,3,H,W) -> (B, n, d)."""
+def tokenize(img: np.ndarray, w: np.ndarray, b: np.ndarray, patch_size: int, emulate=None) -> np.ndarray:
+    """image_to_tokens (:94-97, call :114). img (B,3,H,W) -> (B, n, d).
+    emulate='bf16': operands rounded to bf16 as the engine's tensor-core tokeniser (and autocast) does."""
     B, C, H, W = img.shape
     p = patch_size
     h, wd = H // p, W // p
     x = img.reshape(B, C, h, p, wd, p)            # b c h p1 w p2
     x = x.transpose(0, 2, 4, 3, 5, 1)             # b h w p1 p2 c
     x = x.reshape(B, h * wd, p * p * C)
+    if emulate == "bf16":
+        return (bf16_round(x) @ bf16_round(w).T + b.astype(np.float32)).astype(img.dtype)
     return x @ w.T + b
 
 
@@ -186,7 +189,7 @@ def glom_forward(params, img, *, patch_size, iters=None, levels=None, return_all
     L, d = P["init_levels"].shape
     if tokens is None:
         tokens = tokenize(np.asarray(img, dtype=dtype), P["image_to_tokens.1.weight"],
-                          P["image_to_tokens.1.bias"], patch_size)       # (:114)
+                          P["image_to_tokens.1.bias"], patch_size, emulate)   # (:114)
     else:
         tokens = np.asarray(tokens, dtype=dtype)
     B, n, _ = tokens.shape

@@ -122,7 +122,7 @@ def test_stage_buffers_hidden_and_consensus():
     off, nb = _native.workspace_offset(cfg, B, 1, False, 1)
     C = ws[off:off + nb].view(torch.bfloat16).float().reshape(B, n, L, d).cpu().numpy()
     P = {k: v.astype(np.float32) for k, v in params.items()}
-    tok = O.tokenize(img, P["image_to_tokens.1.weight"], P["image_to_tokens.1.bias"], case["patch_size"])
+    tok = O.tokenize(img, P["image_to_tokens.1.weight"], P["image_to_tokens.1.bias"], case["patch_size"], emulate="bf16")
     S0 = np.broadcast_to(P["init_levels"], (B, n, L, d)).astype(np.float32)
     pos = P["pos_emb.weight"][:n][None, :, None, :]
     lwi = np.concatenate([tok[:, :, None, :], S0], 2)
@@ -153,6 +153,22 @@ def test_native_tokenizer_matches_oracle():
     want = O.tokenize(img.astype(np.float64), params["image_to_tokens.1.weight"].astype(np.float64),
                       params["image_to_tokens.1.bias"].astype(np.float64), case["patch_size"])
     assert tok.shape == want.shape and np.abs(tok - want).max() <= 1e-4
+
+
+def test_tensor_core_tokenizer_matches_oracle():
+    """bf16 precision: patchify + cast + tcgen05 GEMM vs the bf16-operand oracle (and the exact one)."""
+    for name in ("mid_nonsquare", "c1_return_all"):
+        case, params, _ = load(name)
+        m = make_model(case, params, "bf16")
+        img, _ = inputs(case)
+        with torch.no_grad():
+            tok = m.tokens(torch.from_numpy(img).to(DEV)).cpu().numpy()
+        w, b = params["image_to_tokens.1.weight"], params["image_to_tokens.1.bias"]
+        emu = O.tokenize(img, w, b, case["patch_size"], emulate="bf16")
+        exact = O.tokenize(img.astype(np.float64), w.astype(np.float64), b.astype(np.float64), case["patch_size"])
+        assert tok.shape == emu.shape
+        assert np.abs(tok - emu).max() <= 1e-4
+        assert np.abs(tok - exact).max() <= 2e-2 * max(1.0, np.abs(exact).max())
 
 
 # ----------------------------------------------------------------------------- BASELINE sizes

@@ -61,7 +61,7 @@ def stage_bf16_stages(dim=128, L=4, isz=32, p=4, B=2):
     off, nb = _native.workspace_offset(cfg, B, 1, False, 1)
     C = ws[off:off + nb].view(torch.bfloat16).float().reshape(B, n, L, d).cpu().numpy()
     P = {k: v.astype(np.float32) for k, v in params.items()}
-    tok = O.tokenize(img, P["image_to_tokens.1.weight"], P["image_to_tokens.1.bias"], p)
+    tok = O.tokenize(img, P["image_to_tokens.1.weight"], P["image_to_tokens.1.bias"], p, emulate="bf16")
     pos = P["pos_emb.weight"][:n][None, :, None, :]
     lwi = np.concatenate([tok[:, :, None, :], lv], 2)
     w1bu = P["bottom_up.net.1.weight"].reshape(L, 4 * d, d); b1bu = P["bottom_up.net.1.bias"].reshape(L, 4 * d)
