@@ -290,10 +290,18 @@ def main():
                 if k in flops and args.precision == "bf16":
                     kern[k]["tflops"] = flops[k] / (ms / cnt * 1e-3) / 1e12
         dom = "gemm1_gelu"
+        traffic = None
+        try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f)["kernels"][dom]["dram_bytes"] if args.batch_per_gpu == BATCH_PER_GPU else None
+        except (OSError, KeyError, ValueError):
+            traffic = None
         roof = {"bound": "tensor", "kernel": "gemm_kernel<0,256> (grouped GEMM1 + bias + exact-erf GELU, tcgen05)",
                 "achieved": kern.get(dom, {}).get("tflops"), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": (kern[dom]["tflops"] / peaks["tflops"]) if kern.get(dom, {}).get("tflops") else None,
-                "traffic": None, "peak_source": peaks["source"],
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read+write)",
+                "algorithmic_bytes": rows * d * 2 * G_ + G_ * 4 * d * d * 2 + rows * G_ * 4 * d * 2,
+                "peak_source": peaks["source"],
                 "flops_per_launch": flops[dom],
                 "whole_step": {"tflops": flops_per_col_iter(d, L, N_PATCH) * col_iters_step / world /
                                (ms_dev / args.steps * 1e-3) / 1e12,
