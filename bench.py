@@ -115,6 +115,8 @@ def run_reference_arm(args, rank, world):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock, power and throttle reasons DURING the timed region: an NVML polling thread (every
+    ~5 ms); falls back to `nvidia-smi -lms` if pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -122,8 +124,44 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.thread = None
+        self.samples = []
+        self._stop = False
+        self.max_mhz = None
+
+    def _poll(self):
+        import pynvml
+        h = self.handle
+        while not self._stop:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -132,6 +170,23 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            import pynvml
+            self._stop = True
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            bits = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            pmax = max(p for _, p, _ in self.samples)
+            load = [s for s in self.samples if s[1] > 0.5 * pmax] or self.samples
+            reasons = sorted(k for k, b in bits.items() if any(s[2] & b for s in load))
+            return {"sm_mhz": statistics.median(s[0] for s in load), "sm_max_mhz": self.max_mhz,
+                    "power_w_max": pmax, "power_w_median_under_load": statistics.median(s[1] for s in load),
+                    "samples": len(self.samples), "samples_under_load": len(load), "reasons": reasons,
+                    "how": "NVML polled every ~5 ms during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -158,14 +213,14 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------ ours
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
@@ -252,17 +307,43 @@ def main():
         prof = _native.profile_end()
         clocks = sampler.stop() if rank == 0 else None
 
-        # -------- end to end through the public API with host buffers
-        for i in range(2):
-            out = model(host_imgs[i % NBUF].to(dev, non_blocking=True), iters=T)
-            host_out.copy_(out, non_blocking=True)
+        # -------- end to end through the public API with host buffers: every step copies its images from pinned
+        # host memory and its result back to pinned host memory inside the timed region.  Copies run on a second
+        # stream, double-buffered, so step i's D2H and step i+1's H2D overlap step i+1's compute.
+        copy_stream = torch.cuda.Stream(dev)
+        host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+
+        def e2e_loop(nsteps):
+            staged = None
+            ready = torch.cuda.Event()
+            with torch.cuda.stream(copy_stream):
+                staged = host_imgs[0].to(dev, non_blocking=True)
+                ready.record(copy_stream)
+            for i in range(nsteps):
+                stream.wait_event(ready)                       # this step's images are on the device
+                x = staged
+                if i + 1 < nsteps:                             # prefetch the next step's images
+                    nxt_ready = torch.cuda.Event()
+                    with torch.cuda.stream(copy_stream):
+                        staged = host_imgs[(i + 1) % NBUF].to(dev, non_blocking=True)
+                        nxt_ready.record(copy_stream)
+                out = model(x, iters=T)                        # public API call on the compute stream
+                done = torch.cuda.Event()
+                done.record(stream)
+                x.record_stream(stream)
+                with torch.cuda.stream(copy_stream):           # result back to the host
+                    copy_stream.wait_event(done)
+                    host_outs[i % 2].copy_(out, non_blocking=True)
+                    out.record_stream(copy_stream)
+                if i + 1 < nsteps:
+                    ready = nxt_ready
+            stream.wait_stream(copy_stream)                    # the last D2H is inside the timed region
+
+        e2e_loop(2)
         barrier()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ee0.record(stream)
-        for i in range(args.steps):
-            x = host_imgs[i % NBUF].to(dev, non_blocking=True)
-            out = model(x, iters=T)
-            host_out.copy_(out, non_blocking=True)
+        e2e_loop(args.steps)
         ee1.record(stream)
         barrier()
         ms_e2e = ee0.elapsed_time(ee1)

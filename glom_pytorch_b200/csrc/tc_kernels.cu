@@ -342,15 +342,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
     constexpr int PART_COLS = Cfg::PART_COLS;
     uint8_t* patch = patches + (size_t)ew * Cfg::PATCH_BYTES;
     int as = 0; uint32_t aphase = 0;
+    // the next tile's bias row is fetched into registers one tile ahead, so its (L2-latency) load overlaps this
+    // tile's epilogue instead of sitting on the critical path; it is swapped into shared memory between tiles
+    auto bias_src = [&](int tile_id) -> const float* {
+      const TileInfo tt = decode_tile<MODE>(p, tile_id);
+      return (MODE == 0) ? p.bias + (size_t)tt.z * 4 * p.d + tt.n_blk * BN : p.bias + (size_t)tt.z * p.d + tt.n_blk * BN;
+    };
+    constexpr int BIAS_PER_THREAD = (BN + EPI_THREADS - 1) / EPI_THREADS;
+    if (cluster_id < p.num_tiles) {
+      const float* bsrc = bias_src(cluster_id);
+      for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
+    }
+    named_bar_sync(1, EPI_THREADS);
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       const TileInfo t = decode_tile<MODE>(p, tile);
-      // stage this tile's bias row in shared memory while the MMAs run
-      {
-        const float* bsrc = (MODE == 0) ? p.bias + (size_t)t.z * 4 * p.d + t.n_blk * BN
-                                        : p.bias + (size_t)t.z * p.d + t.n_blk * BN;   // MODE 2: z == 0
-        named_bar_sync(1, EPI_THREADS);          // everyone is done with the previous tile's bias
-        for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
-        named_bar_sync(1, EPI_THREADS);
+      float next_bias[BIAS_PER_THREAD];
+      const bool has_next = tile + num_clusters < p.num_tiles;
+      if (has_next) {
+        const float* bsrc = bias_src(tile + num_clusters);
+#pragma unroll
+        for (int i = 0; i < BIAS_PER_THREAD; ++i)
+          next_bias[i] = (et + i * EPI_THREADS < BN) ? __ldg(bsrc + et + i * EPI_THREADS) : 0.f;
       }
       const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
       const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
@@ -408,6 +420,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (has_next) {
+        named_bar_sync(1, EPI_THREADS);     // everyone is done with this tile's bias
+#pragma unroll
+        for (int i = 0; i < BIAS_PER_THREAD; ++i)
+          if (et + i * EPI_THREADS < BN) bias_s[et + i * EPI_THREADS] = next_bias[i];
+        named_bar_sync(1, EPI_THREADS);     // next tile's bias visible
+      }
     }
   }
 
