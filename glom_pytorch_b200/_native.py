@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libglom_b200.so")
+LIB_PATH = os.environ.get("GLOM_B200_LIB") or os.path.join(_PKG, "libglom_b200.so")   # override: A/B timing of builds
 
 ABI_VERSION = 1
 PRECISION = {"fp32": 0, "bf16": 1}

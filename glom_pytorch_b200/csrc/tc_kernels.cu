@@ -92,6 +92,33 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   return t;
 }
 
+// Static tile schedule of cluster `c` (of `C`): the it-th tile it processes, or -1 when done.
+//   K1 / tokeniser: uniform tiles, plain round-robin.
+//   K2: the top level's tiles cost half (K = 4d instead of 8d, :137).  Full-cost tiles are dealt round-robin
+//   first; the half-cost ones then go to the clusters that received one full tile fewer (up to two each, which
+//   levels them with the others) and only after that round-robin over everybody.  Closed form, so every warp
+//   role of both CTAs walks the same list without communication.
+template <int MODE>
+__device__ __forceinline__ int sched_tile(const GemmParams& p, int c, int C, int it) {
+  if (MODE != 1) { const int t = c + it * C; return t < p.num_tiles ? t : -1; }
+  const int S = p.num_m * p.num_n;            // half-cost tiles (top level), ids [B, B + S)
+  const int B = p.num_tiles - S;              // full-cost tiles, ids [0, B)
+  const int heavy = B % C;                    // clusters [0, heavy) hold one more full tile than the rest
+  const int nb = (B - c + C - 1) / C;         // full tiles of this cluster (B - c may be <= 0)
+  const int nbig = nb > 0 ? nb : 0;
+  if (it < nbig) return c + it * C;
+  int k = it - nbig;                          // k-th half-cost tile of this cluster
+  const int light = C - heavy;
+  const int first = (2 * light < S) ? 2 * light : S;     // half tiles dealt to the light clusters first
+  if (c >= heavy) {
+    if (k < 2) { const int j = k * light + (c - heavy); if (j < first) return B + j; }
+    k -= 2;
+    if (k < 0) return -1;
+  }
+  const int j = first + k * C + c;            // the rest: round-robin over all clusters
+  return j < S ? B + j : -1;
+}
+
 // Sum of squares of a 32-column chunk row, in the canonical order shared with prep_state_kernel:
 // 8 lanes hold 4 consecutive columns each (sequential fmaf), then an xor tree over the 8 lanes.
 __device__ __forceinline__ float row_chunk_sumsq(float a, float b, float c, float d) {
@@ -274,7 +301,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
         const TileInfo t = decode_tile<MODE>(p, tile);
         const CUtensorMap* amap;
         int a_col, b_row;
@@ -310,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
         const TileInfo t = decode_tile<MODE>(p, tile);
         mbar_wait(&tempty_bar[as], aphase ^ 1);      // both CTAs' epilogues drained this accumulator stage
         tc_fence_after_sync();
@@ -349,17 +376,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       return (MODE == 0) ? p.bias + (size_t)tt.z * 4 * p.d + tt.n_blk * BN : p.bias + (size_t)tt.z * p.d + tt.n_blk * BN;
     };
     constexpr int BIAS_PER_THREAD = (BN + EPI_THREADS - 1) / EPI_THREADS;
-    if (cluster_id < p.num_tiles) {
-      const float* bsrc = bias_src(cluster_id);
+    if (sched_tile<MODE>(p, cluster_id, num_clusters, 0) >= 0) {
+      const float* bsrc = bias_src(sched_tile<MODE>(p, cluster_id, num_clusters, 0));
       for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
     }
     named_bar_sync(1, EPI_THREADS);
-    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+    for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
       const TileInfo t = decode_tile<MODE>(p, tile);
       float next_bias[BIAS_PER_THREAD];
-      const bool has_next = tile + num_clusters < p.num_tiles;
+      const int next_tile = sched_tile<MODE>(p, cluster_id, num_clusters, it + 1);
+      const bool has_next = next_tile >= 0;
       if (has_next) {
-        const float* bsrc = bias_src(tile + num_clusters);
+        const float* bsrc = bias_src(next_tile);
 #pragma unroll
         for (int i = 0; i < BIAS_PER_THREAD; ++i)
           next_bias[i] = (et + i * EPI_THREADS < BN) ? __ldg(bsrc + et + i * EPI_THREADS) : 0.f;

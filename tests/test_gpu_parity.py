@@ -171,6 +171,41 @@ def test_tensor_core_tokenizer_matches_oracle():
         assert np.abs(tok - exact).max() <= 2e-2 * max(1.0, np.abs(exact).max())
 
 
+EDGE = [
+    # dim, L, image_size, patch, img_hw, batch, iters, kwargs
+    (192, 3, 24, 4, (24, 24), 2, 2, {}),                       # d % 128 != 0  -> 64-wide GEMM2 tiles, n = 36
+    (320, 2, 16, 4, (16, 16), 3, 2, {}),                       # d = 5 x 64: attention output slices 256 + 64
+    (64, 3, 224, 14, (140, 140), 3, 2, {}),                    # n = 100 of 256: ragged key padding, rows % 128 != 0
+    (128, 3, 96, 4, (96, 96), 1, 2, {}),                       # n = 576: three key blocks, online max across blocks
+    (128, 4, 64, 4, (64, 64), 1, 2, dict(local_consensus_radius=3)),   # radius mask on a 16 x 16 grid (n = 256)
+    (64, 2, 8, 4, (8, 8), 1, 3, dict(consensus_self=True)),    # n = 4: a single 16-key block mostly padding
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("spec", EDGE, ids=[f"d{e[0]}_L{e[1]}_hw{e[4][0]}x{e[4][1]}_p{e[3]}" for e in EDGE])
+def test_shape_edge_cases_against_oracle(spec, precision):
+    """Ragged / extreme shapes the reference accepts: checked against the fp64 CPU oracle."""
+    dim, L, isz, p, hw, B, T, kw = spec
+    params = O.synth_params(dim, L, isz, p, seed=3)
+    m = G.Glom(dim=dim, levels=L, image_size=isz, patch_size=p, precision=precision, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+    m = m.to(DEV).eval()
+    rng = np.random.default_rng(5)
+    img = rng.standard_normal((B, 3) + hw).astype(np.float32)
+    n = (hw[0] // p) * (hw[1] // p)
+    lv = (rng.standard_normal((B, n, L, dim)) * 2).astype(np.float32)
+    with torch.no_grad():
+        out = m(torch.from_numpy(img).to(DEV), iters=T, levels=torch.from_numpy(lv).to(DEV),
+                return_all=True).cpu().numpy()
+    ref = O.glom_forward(params, img, patch_size=p, iters=T, levels=lv, return_all=True, image_size=isz,
+                         dtype=np.float64, **kw)
+    if precision == "fp32":
+        assert np.abs(out - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    else:
+        check_bf16(out, ref, spec)
+
+
 # ----------------------------------------------------------------------------- BASELINE sizes
 FULL = dict(dim=512, levels=6, image_size=224, patch_size=14)
 
