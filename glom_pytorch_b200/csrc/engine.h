@@ -58,7 +58,7 @@ struct WorkspaceLayout {
   size_t sb_off[2];    // bf16 shadow of the state           (rows, L, d)
   size_t sp_off[2];    // bf16 shadow of state[:, :, 1:] + pos (rows, L-1, d)
   size_t xb_off;       // bf16 tokens                        (rows, d)
-  size_t h_off;        // hidden activations                 (rows, G*4d)   bf16 | f32
+  size_t h_off;        // hidden activations: bf16 engine = 16 KB blocks [G][rows/128][4d/64][128][64]; f32 = (rows, G*4d)
   size_t h_bytes;
   size_t c_off;        // consensus output                   (rows, L, d)   bf16 | f32
   size_t c_bytes;

@@ -46,7 +46,7 @@ WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, in
     for (int i = 0; i < 2; ++i) { w.sb_off[i] = off; off = align_up(off + state_elems * 2, 1024); }
     for (int i = 0; i < 2; ++i) { w.sp_off[i] = off; off = align_up(off + (size_t)g.rows * (g.L - 1) * g.d * 2, 1024); }
     w.xb_off = off; off = align_up(off + (size_t)g.rows * g.d * 2, 1024);
-    w.h_bytes = (size_t)g.rows * g.G * 4 * g.d * 2;
+    w.h_bytes = (size_t)((g.rows + 127) / 128 * 128) * g.G * 4 * g.d * 2;   // 128-row blocks, padded
     w.c_bytes = state_elems * 2;
     w.nsq_bytes = (size_t)g.rows * g.L * g.nparts * 4;
   } else {

@@ -38,6 +38,7 @@ constexpr int GEMM_CTRL_WARPS = 4;
 struct GemmParams {
   int rows, d, L, n, G;
   int num_m, num_n, num_tiles;       // num_m counts 256-row pair tiles
+  int m128;                          // 128-row blocks of the (padded) hidden buffer H
   const float* bias;
   // K1
   __nv_bfloat16* h_out;
@@ -312,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           else { amap = &map_a1; a_col = (l - 1) * p.d; }                     // bottom-up l reads S[l-1]   (:134)
           b_row = t.z * 4 * p.d + t.n_blk * BN;
         } else if (MODE == 1) {
-          amap = &map_a0; a_col = 2 * t.z * 4 * p.d;
+          amap = &map_a0; a_col = 0;             // H is stored as contiguous 16 KB (128 x 64) blocks, see below
           b_row = t.z * p.d + t.n_blk * BN;
         } else {
           amap = &map_a0; a_col = 0;               // patches (rows, Kp) x Wtok (d, Kp)
@@ -325,7 +326,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land here
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
+          if (MODE == 1) {
+            // block (group g, 128-row block, 64-wide k block): [H_bu,l | H_td,l] are groups 2l and 2l+1
+            const int kbg_n = 4 * p.d / BK;
+            const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
+            const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
+            tma_load_2d_2sm(sa, amap, bar, 0, blk * BM);
+          } else {
+            tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
+          }
           tma_load_2d_2sm(sa + A_STAGE_BYTES, &map_b, bar, kb * BK, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -399,14 +408,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
       const float* bias = bias_s + part * PART_COLS;
       if (MODE == 0) {
-        __nv_bfloat16* hrow = p.h_out + (size_t)row0 * p.G * 4 * p.d + (size_t)t.z * 4 * p.d + t.n_blk * BN + part * PART_COLS;
+        // H block (group, 128-row block, k block = this warp's 64-column part): 16 KB contiguous, row pitch 64
+        const int hblk = (t.z * p.m128 + (t.m_blk * 2 + (int)cta_rank)) * (4 * p.d / BK) + t.n_blk * (BN / BK) + part;
+        __nv_bfloat16* hrow = p.h_out + ((size_t)hblk * BM + quad * 32) * BK;
 #pragma unroll 1
         for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
-          if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, 32);
-          else k1_chunk<false>(v, bias + c0, patch, hrow + c0, (size_t)p.G * 4 * p.d, lane, rows_left);
+          if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, 32);
+          else k1_chunk<false>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, rows_left);
         }
       } else if (MODE == 2) {
         float* trow = p.tok_out + (size_t)row0 * p.d + t.n_blk * BN + part * PART_COLS;
@@ -834,7 +845,8 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
   // ---------------- K1: grouped GEMM1 + bias + GELU -> H
   CUtensorMap mh;
-  if (!map2d(enc, &mh, b.h, rows, (uint64_t)g.G * 4 * d, BM, err, errlen, "H")) return -3;
+  const int m128 = (rows + BM - 1) / BM;
+  if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
   {
     CUtensorMap mx, msb, msp, mw1;
     if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
@@ -844,7 +856,7 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     GemmParams p{};
     p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
     p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
-    p.bias = b.b1; p.h_out = b.h;
+    p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
     ProfScope scope(prof, PROF_GEMM1, st);
     cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
     if (launches) ++*launches;
@@ -900,6 +912,7 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     GemmParams p{};
     p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
     p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
+    p.m128 = m128;
     p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
     p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
     { const char* pv = getenv("GLOM_B200_PROBE"); p.probe = pv ? atoi(pv) : 0; }

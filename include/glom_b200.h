@@ -125,7 +125,9 @@ GLOM_B200_API int glom_b200_last_launch_count(void);
 
 /* Diagnostics: byte offsets of intermediate buffers inside the workspace for the same
  * (cfg, batch, iters, return_all); tests use them to check single stages.
- * which: 0 = hidden activations H (rows, (2L-1)*4d), 1 = consensus C (rows, L, d),
+ * which: 0 = hidden activations H -- bf16 engine: 16 KB blocks [2L-1][ceil(rows/128)][4d/64][128][64]
+ *            (group, 128-row block, 64-column block, row, column), fp32 engine: (rows, (2L-1)*4d);
+ *        1 = consensus C (rows, L, d),
  *        2 = squared-norm partials. Returns GLOM_B200_ERR_INVALID for unknown ids. */
 GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch, int iters, int return_all,
                                int which, size_t* out_offset, size_t* out_bytes);

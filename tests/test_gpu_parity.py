@@ -118,7 +118,9 @@ def test_stage_buffers_hidden_and_consensus():
     cfg = m.engine_cfg(n)
     ws = m._workspace
     off, nb = _native.workspace_offset(cfg, B, 1, False, 0)
-    H = ws[off:off + nb].view(torch.bfloat16).float().reshape(B * n, 2 * L - 1, 4 * d).cpu().numpy()
+    m128 = (B * n + 127) // 128
+    H = ws[off:off + nb].view(torch.bfloat16).float().reshape(2 * L - 1, m128, 4 * d // 64, 128, 64)
+    H = H.permute(1, 3, 0, 2, 4).reshape(m128 * 128, 2 * L - 1, 4 * d)[:B * n].cpu().numpy()   # (row, group, 4d)
     off, nb = _native.workspace_offset(cfg, B, 1, False, 1)
     C = ws[off:off + nb].view(torch.bfloat16).float().reshape(B, n, L, d).cpu().numpy()
     P = {k: v.astype(np.float32) for k, v in params.items()}
