@@ -53,9 +53,32 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
     return out
 
 
-def gelu_erf(x: np.ndarray) -> np.ndarray:
-    """nn.GELU() default = 0.5 x (1 + erf(x / sqrt 2))   (glom_pytorch.py:30)."""
+_POOL = None
+
+
+def _gelu_block(x):
     return (0.5 * x * (1.0 + _erf(x * x.dtype.type(1.0 / math.sqrt(2.0))))).astype(x.dtype)
+
+
+def gelu_erf(x: np.ndarray) -> np.ndarray:
+    """nn.GELU() default = 0.5 x (1 + erf(x / sqrt 2))   (glom_pytorch.py:30).
+    Large inputs are split over a thread pool (the erf ufunc releases the GIL) so that the CPU port
+    used as bench.py's baseline is not single-threaded in its second-largest cost."""
+    global _POOL
+    if x.ndim != 2 or x.shape[0] < 512:
+        return _gelu_block(x)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nthreads = min(32, os.cpu_count() or 1)
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=nthreads)
+    out = np.empty_like(x)
+    step = -(-x.shape[0] // nthreads)
+
+    def work(i):
+        out[i:i + step] = _gelu_block(x[i:i + step])
+    list(_POOL.map(work, range(0, x.shape[0], step)))
+    return out
 
 
 def synth_params(dim, levels, image_size, patch_size, seed=0, dtype=np.float32):
