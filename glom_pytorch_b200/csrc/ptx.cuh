@@ -215,6 +215,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
       : "memory");
 }
 
+// Programmatic dependent launch: `pdl_wait` blocks until the preceding kernel in the stream has completed and its
+// writes are visible; everything before it (barrier init, TMEM allocation, descriptor prefetch) overlaps that
+// kernel's tail.  `pdl_launch_dependents` lets the next kernel's CTAs be scheduled as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- small math helpers

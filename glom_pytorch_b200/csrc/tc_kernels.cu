@@ -39,6 +39,8 @@ struct GemmParams {
   int rows, d, L, n, G;
   int num_m, num_n, num_tiles;       // num_m counts 256-row pair tiles
   int m128;                          // 128-row blocks of the (padded) hidden buffer H
+  int z0;                            // first MLP group (K1) / level (K2) of this launch, see level batching below
+  int n_half;                        // K2: number of half-cost (top-level) tiles in this launch
   const float* bias;
   // K1
   __nv_bfloat16* h_out;
@@ -86,7 +88,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   t.n_blk = tile % p.num_n;
   const int r = tile / p.num_n;
   t.m_blk = r % p.num_m;
-  t.z = r / p.num_m;
+  t.z = p.z0 + r / p.num_m;
   if (MODE == 0) t.num_kb = p.d / BK;
   else if (MODE == 1) t.num_kb = ((t.z == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;   // top level: no top-down half (:137)
   else t.num_kb = p.tok_kb;
@@ -102,7 +104,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
 template <int MODE>
 __device__ __forceinline__ int sched_tile(const GemmParams& p, int c, int C, int it) {
   if (MODE != 1) { const int t = c + it * C; return t < p.num_tiles ? t : -1; }
-  const int S = p.num_m * p.num_n;            // half-cost tiles (top level), ids [B, B + S)
+  const int S = p.n_half;                     // half-cost tiles (top level, last in the launch), ids [B, B + S)
   const int B = p.num_tiles - S;              // full-cost tiles, ids [0, B)
   const int heavy = B % C;                    // clusters [0, heavy) hold one more full tile than the rest
   const int nb = (B - c + C - 1) / C;         // full tiles of this cluster (B - c may be <= 0)
@@ -297,6 +299,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   cluster_sync_all();          // peer barriers initialised + both TMEM allocations done before any cross-CTA traffic
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();     // the next kernel may start its own set-up on SMs we vacate
+  pdl_wait();                  // ... and we touch global memory only after the previous kernel has finished
 
   if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -542,6 +546,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == W_TMA) {
     if (lane == 0) {
@@ -833,36 +839,51 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, BN>, a0, a1, a2, bm, p);
 }
 
 int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
               char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
-  // ---------------- K1: grouped GEMM1 + bias + GELU -> H
+  // Level batching: the hidden activations of `level_batch` levels at a time (67 MB per level at configs[1]) are
+  // produced by K1 and consumed by K2 back to back, so that H is read from L2 instead of making a 2 x 369 MB
+  // round trip through HBM every iteration.  K3 (consensus) runs once, before the first K2.
+  static int level_batch_env = -1;
+  if (level_batch_env < 0) { const char* e = getenv("GLOM_B200_LEVEL_BATCH"); level_batch_env = e ? atoi(e) : 0; }
+  const int level_batch = level_batch_env > 0 ? level_batch_env : L;
   CUtensorMap mh;
   const int m128 = (rows + BM - 1) / BM;
   if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
-  {
-    CUtensorMap mx, msb, msp, mw1;
-    if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
-    if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
-    if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
-    if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
-    GemmParams p{};
-    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = g.G * p.num_m * p.num_n;
-    p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
-    ProfScope scope(prof, PROF_GEMM1, st);
-    cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
-    if (launches) ++*launches;
-    if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
-  }
-  // ---------------- K3: consensus attention -> C  (after K1 so that C is still L2-resident when K2's combine reads it)
+  CUtensorMap mx, msb, msp, mw1, mw2;
+  if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
+  if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
+  if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
+  if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
+  if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2 / 2, err, errlen, "W2p")) return -3;
+  bool attn_done = false;
+  for (int l0 = 0; l0 < L; l0 += level_batch) {
+    const int l1 = (l0 + level_batch < L) ? l0 + level_batch : L;
+    // ---------------- K1: grouped GEMM1 + bias + GELU -> H   (groups of levels [l0, l1))
+    {
+      const int g0 = 2 * l0, g1 = (2 * l1 < g.G) ? 2 * l1 : g.G;
+      GemmParams p{};
+      p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+      p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.z0 = g0; p.num_tiles = (g1 - g0) * p.num_m * p.num_n;
+      p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
+      ProfScope scope(prof, PROF_GEMM1, st);
+      cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
+      if (launches) ++*launches;
+      if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
+    }
+    if (!attn_done) {
+      attn_done = true;
+      // ---------------- K3: consensus attention -> C  (after the first K1 so that C is still L2-resident for K2)
   {
     AttnParams ap{};
     ap.n = n; ap.L = L; ap.d = d;
@@ -900,29 +921,38 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
     dim3 grid((n + BM - 1) / BM, L, g.B);
     ProfScope scope(prof, PROF_ATTN, st);
-    attn_kernel<<<grid, ATTN_THREADS, smem, st>>>(mq, mk, mv, ap);
+    {
+      cudaLaunchConfig_t acfg{};
+      acfg.gridDim = grid; acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
+      cudaLaunchAttribute aattr[1];
+      aattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
+      aattr[0].val.programmaticStreamSerializationAllowed = 1;
+      acfg.attrs = aattr; acfg.numAttrs = 1;
+      cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
+    }
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
   }
-  // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)
-  {
-    CUtensorMap mw2;
-    if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2 / 2, err, errlen, "W2p")) return -3;
-    GemmParams p{};
-    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.num_tiles = L * p.num_m * p.num_n;
-    p.m128 = m128;
-    p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
-    p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
-    { const char* pv = getenv("GLOM_B200_PROBE"); p.probe = pv ? atoi(pv) : 0; }
-    cudaError_t e;
-    ProfScope scope(prof, PROF_GEMM2, st);
-    if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
-    else if (g.bn2 == 128) e = launch_gemm<1, 128>(mh, mh, mh, mw2, p, num_sms, st);
-    else e = launch_gemm<1, 64>(mh, mh, mh, mw2, p, num_sms, st);
-    if (launches) ++*launches;
-    if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
+    }
+    // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)   (levels [l0, l1))
+    {
+      GemmParams p{};
+      p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+      p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.z0 = l0; p.num_tiles = (l1 - l0) * p.num_m * p.num_n;
+      p.n_half = (l1 == L) ? p.num_m * p.num_n : 0;
+      p.m128 = m128;
+      p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+      p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+      { const char* pv = getenv("GLOM_B200_PROBE"); p.probe = pv ? atoi(pv) : 0; }
+      cudaError_t e;
+      ProfScope scope(prof, PROF_GEMM2, st);
+      if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
+      else if (g.bn2 == 128) e = launch_gemm<1, 128>(mh, mh, mh, mw2, p, num_sms, st);
+      else e = launch_gemm<1, 64>(mh, mh, mh, mw2, p, num_sms, st);
+      if (launches) ++*launches;
+      if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
+    }
   }
   return 0;
 }
