@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <mutex>
 #include <vector>
 
 namespace glom {
@@ -115,6 +116,25 @@ cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16
                                  int H, int W, int p, int d, int kp, cudaStream_t st, int* launches);
 int tokenize_tc(const __nv_bfloat16* patches, const __nv_bfloat16* wtok, const float* bias, float* tokens, int rows,
                 int d, int kp, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and per function: remember, per device, the
+// largest size already configured for one kernel (one instance of this per kernel template instantiation).
+struct SmemOptIn {
+  size_t configured[64] = {};
+  std::mutex mu;
+  template <typename K>
+  cudaError_t ensure(K kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes <= configured[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) configured[dev] = bytes;
+    return e;
+  }
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -362,11 +362,10 @@ cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, in
   {
     ProfScope scope(prof, PROF_ATTN, st);
     const size_t smem = (size_t)(AQ * g.d + AQ * g.n) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemOptIn optin;
+    if (smem > 48 * 1024) {
+      cudaError_t e = optin.ensure(attn_f32_kernel, smem);
       if (e != cudaSuccess) return e;
-      configured = smem;
     }
     dim3 grid((g.n + AQ - 1) / AQ, g.L, g.B);
     attn_f32_kernel<<<grid, 256, smem, st>>>(g.n, g.L, g.d, g.attend_self, g.mask_side, g.mask_d2_max, b.s_in, b.c);

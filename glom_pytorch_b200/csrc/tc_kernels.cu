@@ -825,13 +825,8 @@ template <int MODE, int BN>
 static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
                                const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = GemmCfg<MODE, BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (cudaError_t e = optin.ensure(gemm_kernel<MODE, BN>, Cfg::SMEM_BYTES)) return e;
   const int max_clusters = num_sms / 2;
   const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -854,9 +849,9 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
   // Level batching: the hidden activations of `level_batch` levels at a time (67 MB per level at configs[1]) are
   // produced by K1 and consumed by K2 back to back, so that H is read from L2 instead of making a 2 x 369 MB
   // round trip through HBM every iteration.  K3 (consensus) runs once, before the first K2.
-  static int level_batch_env = -1;
-  if (level_batch_env < 0) { const char* e = getenv("GLOM_B200_LEVEL_BATCH"); level_batch_env = e ? atoi(e) : 0; }
-  const int level_batch = level_batch_env > 0 ? level_batch_env : L;
+  const char* lb_env = getenv("GLOM_B200_LEVEL_BATCH");      // tuning knob; default = all levels in one launch pair
+  const int lb = lb_env ? atoi(lb_env) : 0;
+  const int level_batch = (lb > 0 && lb < L) ? lb : L;
   CUtensorMap mh;
   const int m128 = (rows + BM - 1) / BM;
   if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
@@ -905,11 +900,10 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
     ap.num_stages = stages;
     const size_t smem = fixed + (size_t)stages * ATTN_STAGE_BYTES;
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e)); return -3; }
-      configured = smem;
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+      return -3;
     }
     CUtensorMap mq, mk, mv;
     const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
