@@ -53,7 +53,6 @@ struct GemmParams {
   __nv_bfloat16* sp_out;
   float* nsq_out;
   int nparts;
-  int probe;
   // tokeniser (MODE 2)
   float* tok_out;
   int tok_kb;      // K blocks of 64 of the zero-padded patch dimension
@@ -190,7 +189,6 @@ __device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float* 
 // that each lane then owns 4 consecutive columns of 8 rows and every global access covers whole 128-byte lines.
 struct K2Chunk {
   int l, L, d, n, row0;
-  int probe;   // development probe (GLOM_B200_PROBE): 1 = all rows load the same lines, 2 = all rows store to the same lines
   const float* s32_in; const __nv_bfloat16* c_in; const float* pos;
   float* s32_out; __nv_bfloat16* sb_out; __nv_bfloat16* sp_out;
 };
@@ -207,7 +205,6 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
   const bool top = (k.l == k.L - 1);                  // 3 contributions on the top level, 4 elsewhere (:128-129)
   const bool has_td = (k.l >= 1);
   const size_t ld = (size_t)k.L * k.d;
-  const size_t ld_in = (k.probe & 1) ? 0 : ld, ld_out = (k.probe & 2) ? 0 : ld;
   const size_t base = ((size_t)k.row0 * k.L + k.l) * k.d + col + c * 4;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -219,8 +216,8 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
       const int r = (h * 4 + j) * 4 + rsub;
       sv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pp[j] = sv[j]; cw[j] = make_uint2(0u, 0u);
       if (FULL || r < rows_left) {
-        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld_in));
-        cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld_in));
+        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
+        cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld));
         if (has_td) pp[j] = __ldg(reinterpret_cast<const float4*>(k.pos + (size_t)((k.row0 + r) % k.n) * k.d + col + c * 4));
       }
     }
@@ -236,11 +233,11 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float* b
       if (top) { o0 = o0 / 3.0f; o1 = o1 / 3.0f; o2 = o2 / 3.0f; o3 = o3 / 3.0f; }          // (:142) IEEE division
       else { o0 *= 0.25f; o1 *= 0.25f; o2 *= 0.25f; o3 *= 0.25f; }                          // x/4 == x*0.25 exactly
       if (FULL || r < rows_left) {
-        const size_t o = base + (size_t)r * ld_out;
+        const size_t o = base + (size_t)r * ld;
         __stcs(reinterpret_cast<float4*>(k.s32_out + o), make_float4(o0, o1, o2, o3));
         *reinterpret_cast<uint2*>(k.sb_out + o) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         if (has_td)
-          *reinterpret_cast<uint2*>(k.sp_out + ((size_t)(k.row0 + ((k.probe & 2) ? 0 : r)) * (k.L - 1) + (k.l - 1)) * k.d + col + c * 4) =
+          *reinterpret_cast<uint2*>(k.sp_out + ((size_t)(k.row0 + r) * (k.L - 1) + (k.l - 1)) * k.d + col + c * 4) =
               make_uint2(pack_bf16x2(o0 + pp[j].x, o1 + pp[j].y), pack_bf16x2(o2 + pp[j].z, o3 + pp[j].w));
       } else {
         o0 = o1 = o2 = o3 = 0.f;
@@ -323,7 +320,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           amap = &map_a0; a_col = 0;               // patches (rows, Kp) x Wtok (d, Kp)
           b_row = t.n_blk * BN;
         }
-        const int a_row = ((p.probe & 8) ? 0 : t.m_blk * 256) + (int)cta_rank * BM;
+        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
         b_row += (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -434,7 +431,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         }
       } else {
         K2Chunk kc;
-        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = (p.probe & 4) ? 0 : row0; kc.probe = p.probe;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0;
         kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
         kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
         float rowsq[8];
@@ -846,12 +843,10 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
 int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
               char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
-  // Level batching: the hidden activations of `level_batch` levels at a time (67 MB per level at configs[1]) are
-  // produced by K1 and consumed by K2 back to back, so that H is read from L2 instead of making a 2 x 369 MB
-  // round trip through HBM every iteration.  K3 (consensus) runs once, before the first K2.
-  const char* lb_env = getenv("GLOM_B200_LEVEL_BATCH");      // tuning knob; default = all levels in one launch pair
-  const int lb = lb_env ? atoi(lb_env) : 0;
-  const int level_batch = (lb > 0 && lb < L) ? lb : L;
+  // One launch each of K1 (all groups), K3, K2 (all levels).  Splitting K1/K2 into per-level batches so that H stays
+  // L2-resident was measured slower (5.3 / 5.6 / 6.5 ms per step for 3 / 2 / 1 levels per batch vs 5.06 ms): the extra
+  // kernel boundaries and partial waves cost more than the saved HBM traffic (profiles/README.md).
+  const int level_batch = L;
   CUtensorMap mh;
   const int m128 = (rows + BM - 1) / BM;
   if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
@@ -938,7 +933,6 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
       p.m128 = m128;
       p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
       p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
-      { const char* pv = getenv("GLOM_B200_PROBE"); p.probe = pv ? atoi(pv) : 0; }
       cudaError_t e;
       ProfScope scope(prof, PROF_GEMM2, st);
       if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
