@@ -15,6 +15,7 @@ EXPORTS = (
     "glom_b200_pack_weights", "glom_b200_workspace_bytes", "glom_b200_forward",
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
+    "glom_b200_backward", "glom_b200_backward_workspace_bytes",
 )
 PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize")
 
@@ -28,6 +29,12 @@ class Cfg(ctypes.Structure):
 class WeightsRef(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32)] + [
         (k, ctypes.c_void_p) for k in ("bu_w1", "bu_b1", "bu_w2", "bu_b2", "td_w1", "td_b1", "td_w2", "td_b2")]
+
+
+class Grads(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [
+        (k, ctypes.c_void_p) for k in ("d_tokens", "d_pos", "d_state0", "d_init", "d_bu_w1", "d_bu_b1", "d_bu_w2",
+                                       "d_bu_b2", "d_td_w1", "d_td_b1", "d_td_w2", "d_td_b2")]
 
 
 class GlomB200Error(RuntimeError):
@@ -63,6 +70,11 @@ def load():
     lib.glom_b200_profile_begin.restype = i32
     lib.glom_b200_profile_end.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32), i32]
     lib.glom_b200_profile_end.restype = i32
+    lib.glom_b200_backward_workspace_bytes.argtypes = [ctypes.POINTER(Cfg), i32, ctypes.POINTER(sz)]
+    lib.glom_b200_backward_workspace_bytes.restype = i32
+    lib.glom_b200_backward.argtypes = [ctypes.POINTER(Cfg), ctypes.POINTER(WeightsRef), vp, vp, vp, vp,
+                                       ctypes.POINTER(Grads), i32, i32, i32, vp, sz, vp]
+    lib.glom_b200_backward.restype = i32
     for f in ("glom_b200_packed_weight_bytes", "glom_b200_pack_weights", "glom_b200_workspace_bytes",
               "glom_b200_workspace_offset", "glom_b200_forward", "glom_b200_tokenize"):
         getattr(lib, f).restype = i32
@@ -139,3 +151,20 @@ def profile_end():
     cnt = (ctypes.c_int * k)()
     check(load().glom_b200_profile_end(ms, cnt, k))
     return {name: (ms[i], cnt[i]) for i, name in enumerate(PROFILE_KINDS)}
+
+
+def backward_workspace_bytes(cfg, batch):
+    out = ctypes.c_size_t()
+    check(load().glom_b200_backward_workspace_bytes(ctypes.byref(cfg), batch, ctypes.byref(out)))
+    return out.value
+
+
+def backward(cfg, weight_ptrs, tokens_ptr, pos_ptr, states_ptr, grad_out_ptr, grad_ptrs, batch, iters, grad_all,
+             ws_ptr, ws_bytes, stream):
+    """weight_ptrs: the 8 reference-layout tensors; grad_ptrs: dict of the Grads fields (None allowed for
+    d_state0 / d_init)."""
+    w = WeightsRef(ctypes.sizeof(WeightsRef), *weight_ptrs)
+    g = Grads(ctypes.sizeof(Grads), *[grad_ptrs.get(k) for k, _ in Grads._fields_[1:]])
+    check(load().glom_b200_backward(ctypes.byref(cfg), ctypes.byref(w), tokens_ptr, pos_ptr, states_ptr,
+                                    grad_out_ptr, ctypes.byref(g), batch, iters, int(grad_all), ws_ptr, ws_bytes,
+                                    stream))

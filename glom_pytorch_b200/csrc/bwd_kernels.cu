@@ -1,0 +1,422 @@
+// Backward of the GLOM column update (fp32, CUDA cores) -- SURVEY 8 row f2.
+//
+// Differentiates glom_pytorch/glom_pytorch.py:131-145 step by step in reverse, recomputing the per-step
+// intermediates (MLP pre-activations, attention probabilities) from the saved states S_0..S_T instead of
+// storing them:
+//   S_{t+1} = (S_t + BU(S_t, X) + TD(S_t + P) + C(S_t)) / c          (:141-142)
+// All contractions go through one strided, batched fp32 GEMM (NN / NT / TN are just stride choices), the rest
+// are small element-wise / row-reduction kernels.  This is the correctness-grade training path (the fp32
+// precision of the engine); a tensor-core backward is future work.
+#include "engine.h"
+#include "ptx.cuh"
+
+namespace glom {
+
+// =====================================================================================
+// C[z](m, n) = alpha * sum_k A[z](m, k) * B[z](k, n) + beta * C[z](m, n) (+ bias[n])
+// element (i, j) of an operand of batch z = (z / zdiv, z % zdiv) lives at
+//   base + (z / zdiv) * s_b0 + (z % zdiv) * s_b1 + i * s_row + j * s_col
+// =====================================================================================
+struct Mat {
+  const float* p;
+  long long s_row, s_col, s_b0, s_b1;
+};
+struct MatOut {
+  float* p;
+  long long s_row, s_col, s_b0, s_b1;
+};
+struct GemmF32 {
+  int M, N, K, zdiv;
+  Mat A;        // (m, k)
+  Mat B;        // (k, n)
+  MatOut C;     // (m, n)
+  float alpha, beta;
+  const float* bias;   // optional, per n
+};
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 q) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int z = blockIdx.z, z0 = z / q.zdiv, z1 = z % q.zdiv;
+  const float* A = q.A.p + z0 * q.A.s_b0 + z1 * q.A.s_b1;
+  const float* B = q.B.p + z0 * q.B.s_b0 + z1 * q.B.s_b1;
+  float* C = q.C.p + z0 * q.C.s_b0 + z1 * q.C.s_b1;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // pick the load order that walks the operand's unit-stride dimension with consecutive threads
+  const bool a_k_fast = (q.A.s_col == 1), b_k_fast = (q.B.s_row == 1);
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < q.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int kk, rr;
+      if (a_k_fast) { kk = i & 15; rr = i >> 4; } else { rr = i & 63; kk = i >> 6; }
+      As[kk][rr] = (m0 + rr < q.M && k0 + kk < q.K) ? A[(long long)(m0 + rr) * q.A.s_row + (long long)(k0 + kk) * q.A.s_col] : 0.f;
+      if (b_k_fast) { kk = i & 15; rr = i >> 4; } else { rr = i & 63; kk = i >> 6; }
+      Bs[kk][rr] = (n0 + rr < q.N && k0 + kk < q.K) ? B[(long long)(k0 + kk) * q.B.s_row + (long long)(n0 + rr) * q.B.s_col] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= q.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= q.N) continue;
+      float* dst = C + (long long)r * q.C.s_row + (long long)c * q.C.s_col;
+      float v = q.alpha * acc[i][j];
+      if (q.bias) v += q.bias[c];
+      if (q.beta != 0.f) v += q.beta * *dst;
+      *dst = v;
+    }
+  }
+}
+
+static cudaError_t gemm_f32(const GemmF32& q, int batches, cudaStream_t st, int* launches) {
+  dim3 grid((q.M + 63) / 64, (q.N + 63) / 64, batches);
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(q);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// element-wise / reduction helpers
+// =====================================================================================
+// g (R, L, d)  <-  gin (R, L, d) / c_l        (:142);   ds (R, L, d) <- g (residual term of the sum, :141)
+__global__ void scale_by_contrib_kernel(size_t total, int L, int d, const float* __restrict__ gin,
+                                        float* __restrict__ g, float* __restrict__ ds) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int l = (int)((i / d) % L);
+    const float v = gin[i] / ((l == L - 1) ? 3.0f : 4.0f);
+    g[i] = v;
+    ds[i] = v;
+  }
+}
+// xp (R, d) = S[:, l, :] + pos[row % n]     (top-down input, :136)
+__global__ void add_pos_kernel(int rows, int n, int L, int d, int l, const float* __restrict__ s,
+                               const float* __restrict__ pos, float* __restrict__ xp) {
+  const size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / d;
+    const int c = (int)(i % d);
+    xp[i] = s[(r * L + l) * d + c] + pos[(size_t)(r % n) * d + c];
+  }
+}
+// h = gelu(pre) ; dpre = dh * gelu'(pre)   (exact erf form, :30), dpre overwrites dh
+__global__ void gelu_bwd_kernel(size_t total, const float* __restrict__ pre, float* __restrict__ h,
+                                float* __restrict__ dh) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = pre[i];
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    h[i] = x * cdf;
+    dh[i] = dh[i] * (cdf + x * pdf);
+  }
+}
+// out[c] += sum_r src[r * row_stride + c]          (bias gradients)
+__global__ void colsum_acc_kernel(int rows, int cols, long long row_stride, const float* __restrict__ src,
+                                  float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int part = threadIdx.x >> 5;                 // 8 row slices per block
+  __shared__ float red[8][33];
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = part; r < rows; r += 8) acc += src[(long long)r * row_stride + c];
+  red[part][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (part == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
+    out[c] += s;
+  }
+}
+// dpos[nn, c] += sum_b dx[(b * n + nn), c]          (positional-embedding gradient, :136)
+__global__ void pos_grad_kernel(int B, int n, int d, const float* __restrict__ dx, float* __restrict__ dpos) {
+  const size_t total = (size_t)n * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dx[(size_t)b * total + i];
+    dpos[i] += acc;
+  }
+}
+// dst[:, l, :] += src (R, d)
+__global__ void add_into_level_kernel(int rows, int L, int d, int l, const float* __restrict__ src,
+                                      float* __restrict__ dst) {
+  const size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dst[((i / d) * L + l) * d + (i % d)] += src[i];
+}
+__global__ void add_kernel(size_t total, const float* __restrict__ src, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+// khat = S / max(|S|, 1e-12) per (row, level) ; rnorm = 1 / max(|S|, 1e-12)      (F.normalize, :58)
+__global__ void normalize_rows_kernel(int nrows, int d, const float* __restrict__ s, float* __restrict__ khat,
+                                      float* __restrict__ rnorm) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const float* p = s + (size_t)row * d;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) ss = fmaf(p[c], p[c], ss);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = lane; c < d; c += 32) khat[(size_t)row * d + c] = p[c] * r;
+  if (lane == 0) rnorm[row] = r;
+}
+// in-place masked softmax over the last dim of sim (Z, n, n)     (:62-71); one warp per row
+__global__ void attn_softmax_kernel(int Z, int n, int attend_self, int mask_side, int mask_d2_max,
+                                    float* __restrict__ sim) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= Z * n) return;
+  const int i = row % n;
+  float* p = sim + (size_t)row * n;
+  float m = -3.402823466e+38f;
+  for (int j = lane; j < n; j += 32) {
+    float v = p[j];
+    if (!attend_self && j == i) v = -5e-4f;
+    if (mask_side > 0) {
+      const int dh = i / mask_side - j / mask_side, dw = i % mask_side - j % mask_side;
+      if (dh * dh + dw * dw > mask_d2_max) v = -3.402823466e+38f;
+    }
+    p[j] = v;
+    m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) { const float e = expf(p[j] - m); p[j] = e; sum += e; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < n; j += 32) p[j] *= inv;
+}
+// dsim = A * (dA - sum_j A dA), zero where the logit was a constant (diagonal fill, radius mask); in place on dA
+__global__ void attn_softmax_bwd_kernel(int Z, int n, int attend_self, int mask_side, int mask_d2_max,
+                                        const float* __restrict__ A, float* __restrict__ dA) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= Z * n) return;
+  const int i = row % n;
+  const float* a = A + (size_t)row * n;
+  float* g = dA + (size_t)row * n;
+  float dot = 0.f;
+  for (int j = lane; j < n; j += 32) dot = fmaf(a[j], g[j], dot);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int j = lane; j < n; j += 32) {
+    float v = a[j] * (g[j] - dot);
+    if (!attend_self && j == i) v = 0.f;
+    if (mask_side > 0) {
+      const int dh = i / mask_side - j / mask_side, dw = i % mask_side - j % mask_side;
+      if (dh * dh + dw * dw > mask_d2_max) v = 0.f;
+    }
+    g[j] = v;
+  }
+}
+// ds[row] += (dkhat - khat (khat . dkhat)) * rnorm        (backward of F.normalize); one warp per (row, level)
+__global__ void normalize_bwd_kernel(int nrows, int d, const float* __restrict__ khat, const float* __restrict__ dkhat,
+                                     const float* __restrict__ rnorm, float* __restrict__ ds) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const float* k = khat + (size_t)row * d;
+  const float* g = dkhat + (size_t)row * d;
+  float dot = 0.f;
+  for (int c = lane; c < d; c += 32) dot = fmaf(k[c], g[c], dot);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float r = rnorm[row];
+  for (int c = lane; c < d; c += 32) ds[(size_t)row * d + c] += (g[c] - k[c] * dot) * r;
+}
+// dinit[l, c] = sum over rows of g[(row, l, c)]           (broadcast of init_levels, :124)
+__global__ void init_grad_kernel(int rows, int L, int d, const float* __restrict__ g, float* __restrict__ dinit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * d) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += g[(size_t)r * L * d + i];
+  dinit[i] += acc;
+}
+
+static inline int nblk(size_t total, int block = 256) {
+  const size_t want = (total + block - 1) / block;
+  return (int)(want < (size_t)148 * 32 ? (want ? want : 1) : (size_t)148 * 32);
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+#define CKL() do { if (launches) ++*launches; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+BackwardLayout backward_layout(const Geometry& g) {
+  BackwardLayout w{};
+  const size_t state = (size_t)g.rows * g.L * g.d * 4, hid = (size_t)g.rows * 4 * g.d * 4;
+  const size_t attn = (size_t)g.B * g.L * g.n * g.n * 4;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  w.g_off = take(state); w.gs_off = take(state); w.ds_off = take(state);
+  w.khat_off = take(state); w.dkhat_off = take(state);
+  w.rnorm_off = take((size_t)g.rows * g.L * 4);
+  w.pre_off = take(hid); w.h_off = take(hid); w.dh_off = take(hid);
+  w.xp_off = take((size_t)g.rows * g.d * 4); w.dx_off = take((size_t)g.rows * g.d * 4);
+  w.attn_off = take(attn); w.dattn_off = take(attn);
+  w.total = off;
+  return w;
+}
+
+// One reverse step: given gin = dL/dS_{t+1}, produce ds = dL/dS_t (without the external grad of slab t) and
+// accumulate parameter / token / pos gradients.
+static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const float* s_t, const float* gin,
+                                 char* ws, const BackwardLayout& wl, cudaStream_t st, int* launches) {
+  const int R = g.rows, L = g.L, d = g.d, n = g.n, h4 = 4 * g.d;
+  const long long ld = (long long)L * d;
+  float* gs = reinterpret_cast<float*>(ws + wl.gs_off);       // gin / c
+  float* ds = reinterpret_cast<float*>(ws + wl.ds_off);
+  float* pre = reinterpret_cast<float*>(ws + wl.pre_off);
+  float* hb = reinterpret_cast<float*>(ws + wl.h_off);
+  float* dh = reinterpret_cast<float*>(ws + wl.dh_off);
+  float* xp = reinterpret_cast<float*>(ws + wl.xp_off);
+  float* dx = reinterpret_cast<float*>(ws + wl.dx_off);
+  const size_t state = (size_t)R * L * d;
+  scale_by_contrib_kernel<<<nblk(state), 256, 0, st>>>(state, L, d, gin, gs, ds);
+  CKL();
+
+  // ---- the two grouped MLPs (:23-36), one group at a time
+  for (int net = 0; net < 2; ++net) {
+    const int groups = net == 0 ? L : L - 1;
+    const float* w1 = net == 0 ? a.bu_w1 : a.td_w1;
+    const float* b1 = net == 0 ? a.bu_b1 : a.td_b1;
+    const float* w2 = net == 0 ? a.bu_w2 : a.td_w2;
+    float* dw1 = net == 0 ? a.d_bu_w1 : a.d_td_w1;
+    float* db1 = net == 0 ? a.d_bu_b1 : a.d_td_b1;
+    float* dw2 = net == 0 ? a.d_bu_w2 : a.d_td_w2;
+    float* db2 = net == 0 ? a.d_bu_b2 : a.d_td_b2;
+    for (int l = 0; l < groups; ++l) {
+      // input of the group: bottom-up l reads tokens (l == 0) or S[l-1]; top-down l reads S[l+1] + pos
+      Mat X{};
+      if (net == 0 && l == 0) X = Mat{a.tokens, d, 1, 0, 0};
+      else if (net == 0) X = Mat{s_t + (size_t)(l - 1) * d, ld, 1, 0, 0};
+      else {
+        add_pos_kernel<<<nblk((size_t)R * d), 256, 0, st>>>(R, n, L, d, l + 1, s_t, a.pos, xp);
+        CKL();
+        X = Mat{xp, d, 1, 0, 0};
+      }
+      const float* W1 = w1 + (size_t)l * h4 * d;       // (4d, d)
+      const float* W2 = w2 + (size_t)l * d * h4;       // (d, 4d)
+      const Mat DY{gs + (size_t)l * d, ld, 1, 0, 0};   // (R, d) slice of the scaled upstream gradient
+      GemmF32 q{};
+      // pre = X W1^T + b1                                 (R x 4d)
+      q = GemmF32{R, h4, d, 1, X, Mat{W1, 1, d, 0, 0}, MatOut{pre, h4, 1, 0, 0}, 1.f, 0.f, b1 + (size_t)l * h4};
+      CK(gemm_f32(q, 1, st, launches));
+      // dh = DY W2                                        (R x 4d)
+      q = GemmF32{R, h4, d, 1, DY, Mat{W2, h4, 1, 0, 0}, MatOut{dh, h4, 1, 0, 0}, 1.f, 0.f, nullptr};
+      CK(gemm_f32(q, 1, st, launches));
+      gelu_bwd_kernel<<<nblk((size_t)R * h4), 256, 0, st>>>((size_t)R * h4, pre, hb, dh);   // dh := dpre
+      CKL();
+      // dW2 += DY^T h                                     (d x 4d)
+      q = GemmF32{d, h4, R, 1, Mat{DY.p, 1, ld, 0, 0}, Mat{hb, h4, 1, 0, 0}, MatOut{dw2 + (size_t)l * d * h4, h4, 1, 0, 0}, 1.f, 1.f, nullptr};
+      CK(gemm_f32(q, 1, st, launches));
+      colsum_acc_kernel<<<(d + 31) / 32, 256, 0, st>>>(R, d, ld, DY.p, db2 + (size_t)l * d);
+      CKL();
+      // dW1 += dpre^T X                                   (4d x d)
+      q = GemmF32{h4, d, R, 1, Mat{dh, 1, h4, 0, 0}, Mat{X.p, X.s_row, 1, 0, 0}, MatOut{dw1 + (size_t)l * h4 * d, d, 1, 0, 0}, 1.f, 1.f, nullptr};
+      CK(gemm_f32(q, 1, st, launches));
+      colsum_acc_kernel<<<(h4 + 31) / 32, 256, 0, st>>>(R, h4, h4, dh, db1 + (size_t)l * h4);
+      CKL();
+      // dX = dpre W1                                      (R x d)
+      q = GemmF32{R, d, h4, 1, Mat{dh, h4, 1, 0, 0}, Mat{W1, d, 1, 0, 0}, MatOut{dx, d, 1, 0, 0}, 1.f, 0.f, nullptr};
+      CK(gemm_f32(q, 1, st, launches));
+      if (net == 0 && l == 0) {
+        add_kernel<<<nblk((size_t)R * d), 256, 0, st>>>((size_t)R * d, dx, a.d_tokens);
+        CKL();
+      } else if (net == 0) {
+        add_into_level_kernel<<<nblk((size_t)R * d), 256, 0, st>>>(R, L, d, l - 1, dx, ds);
+        CKL();
+      } else {
+        add_into_level_kernel<<<nblk((size_t)R * d), 256, 0, st>>>(R, L, d, l + 1, dx, ds);
+        CKL();
+        pos_grad_kernel<<<nblk((size_t)n * d), 256, 0, st>>>(g.B, n, d, dx, a.d_pos);
+        CKL();
+      }
+    }
+  }
+
+  // ---- consensus attention (:56-73), all (image, level) problems batched
+  {
+    float* khat = reinterpret_cast<float*>(ws + wl.khat_off);
+    float* dkhat = reinterpret_cast<float*>(ws + wl.dkhat_off);
+    float* rnorm = reinterpret_cast<float*>(ws + wl.rnorm_off);
+    float* A = reinterpret_cast<float*>(ws + wl.attn_off);
+    float* dA = reinterpret_cast<float*>(ws + wl.dattn_off);
+    const int Z = g.B * L;
+    const long long sb = (long long)n * ld, sl = d, nn = (long long)n * n;
+    const float scale = 1.0f / sqrtf((float)d);
+    const int wblocks = (R * L * 32 + 255) / 256;
+    normalize_rows_kernel<<<wblocks, 256, 0, st>>>(R * L, d, s_t, khat, rnorm);
+    CKL();
+    GemmF32 q{};
+    // sim = scale * Q Khat^T                              (n x n per (b, l))
+    q = GemmF32{n, n, d, L, Mat{s_t, ld, 1, sb, sl}, Mat{khat, 1, ld, sb, sl}, MatOut{A, n, 1, nn * L, nn}, scale, 0.f, nullptr};
+    CK(gemm_f32(q, Z, st, launches));
+    attn_softmax_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A);
+    CKL();
+    // dA = dC V^T
+    q = GemmF32{n, n, d, L, Mat{gs, ld, 1, sb, sl}, Mat{s_t, 1, ld, sb, sl}, MatOut{dA, n, 1, nn * L, nn}, 1.f, 0.f, nullptr};
+    CK(gemm_f32(q, Z, st, launches));
+    // dV: ds += A^T dC
+    q = GemmF32{n, d, n, L, Mat{A, 1, n, nn * L, nn}, Mat{gs, ld, 1, sb, sl}, MatOut{ds, ld, 1, sb, sl}, 1.f, 1.f, nullptr};
+    CK(gemm_f32(q, Z, st, launches));
+    attn_softmax_bwd_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A, dA);
+    CKL();
+    // dQ: ds += scale * dsim Khat
+    q = GemmF32{n, d, n, L, Mat{dA, n, 1, nn * L, nn}, Mat{khat, ld, 1, sb, sl}, MatOut{ds, ld, 1, sb, sl}, scale, 1.f, nullptr};
+    CK(gemm_f32(q, Z, st, launches));
+    // dKhat = scale * dsim^T Q
+    q = GemmF32{n, d, n, L, Mat{dA, 1, n, nn * L, nn}, Mat{s_t, ld, 1, sb, sl}, MatOut{dkhat, ld, 1, sb, sl}, scale, 0.f, nullptr};
+    CK(gemm_f32(q, Z, st, launches));
+    normalize_bwd_kernel<<<wblocks, 256, 0, st>>>(R * L, d, khat, dkhat, rnorm, ds);
+    CKL();
+  }
+  return cudaSuccess;
+}
+
+cudaError_t backward_f32(const Geometry& g, const BackwardArgs& a, int iters, int grad_all, void* workspace,
+                         cudaStream_t st, int* launches) {
+  const BackwardLayout wl = backward_layout(g);
+  char* ws = static_cast<char*>(workspace);
+  const size_t state = (size_t)g.rows * g.L * g.d;
+  float* G = reinterpret_cast<float*>(ws + wl.g_off);
+  float* ds = reinterpret_cast<float*>(ws + wl.ds_off);
+  // G = dL/dS_T
+  const float* top = grad_all ? a.grad_out + (size_t)iters * state : a.grad_out;
+  CK(cudaMemcpyAsync(G, top, state * 4, cudaMemcpyDeviceToDevice, st));
+  for (int t = iters - 1; t >= 0; --t) {
+    CK(backward_step(g, a, a.states + (size_t)t * state, G, ws, wl, st, launches));
+    CK(cudaMemcpyAsync(G, ds, state * 4, cudaMemcpyDeviceToDevice, st));
+    if (grad_all) {
+      add_kernel<<<nblk(state), 256, 0, st>>>(state, a.grad_out + (size_t)t * state, G);
+      CKL();
+    }
+  }
+  if (a.d_state0) {
+    add_kernel<<<nblk(state), 256, 0, st>>>(state, G, a.d_state0);
+    CKL();
+  }
+  if (a.d_init) {
+    init_grad_kernel<<<(g.L * g.d + 255) / 256, 256, 0, st>>>(g.rows, g.L, g.d, G, a.d_init);
+    CKL();
+  }
+  return cudaSuccess;
+}
+
+}  // namespace glom

@@ -117,6 +117,25 @@ cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16
 int tokenize_tc(const __nv_bfloat16* patches, const __nv_bfloat16* wtok, const float* bias, float* tokens, int rows,
                 int d, int kp, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen);
 
+// ---- backward (fp32, CUDA cores; bwd_kernels.cu) ---------------------------------------------------------
+struct BackwardArgs {
+  const float* tokens;   // (R, d)
+  const float* pos;      // (n, d)
+  const float* states;   // (T+1, R, L, d): S_0 .. S_T of the forward
+  const float* grad_out; // (T+1, R, L, d) if grad_all else (R, L, d): dL/d(returned tensor)
+  const float *bu_w1, *bu_b1, *bu_w2, *td_w1, *td_b1, *td_w2;   // reference layout, fp32
+  // outputs, ACCUMULATED into (caller zero-initialises); d_state0 / d_init: exactly one is non-NULL
+  float *d_tokens, *d_pos, *d_state0, *d_init;
+  float *d_bu_w1, *d_bu_b1, *d_bu_w2, *d_bu_b2, *d_td_w1, *d_td_b1, *d_td_w2, *d_td_b2;
+};
+struct BackwardLayout {
+  size_t g_off, gs_off, ds_off, khat_off, dkhat_off, rnorm_off, pre_off, h_off, dh_off, xp_off, dx_off, attn_off,
+      dattn_off, total;
+};
+BackwardLayout backward_layout(const Geometry& g);
+cudaError_t backward_f32(const Geometry& g, const BackwardArgs& a, int iters, int grad_all, void* workspace,
+                         cudaStream_t st, int* launches);
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and per function: remember, per device, the
 // largest size already configured for one kernel (one instance of this per kernel template instantiation).
 struct SmemOptIn {

@@ -307,6 +307,46 @@ GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, cons
   return 0;
 }
 
+GLOM_B200_API int glom_b200_backward_workspace_bytes(const glom_b200_cfg* cfg, int batch, size_t* out_bytes) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || !out_bytes) return fail(GLOM_B200_ERR_INVALID, "bad batch/out_bytes");
+  *out_bytes = backward_layout(make_geometry(cfg, batch)).total;
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_weights_ref* w, const float* tokens,
+                                     const float* pos, const float* states, const float* grad_out,
+                                     const glom_b200_grads* gr, int batch, int iters, int grad_all, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || iters < 0) return fail(GLOM_B200_ERR_INVALID, "batch must be >= 1 and iters >= 0");
+  if (!w || w->struct_size != sizeof(glom_b200_weights_ref) || !gr || gr->struct_size != sizeof(glom_b200_grads))
+    return fail(GLOM_B200_ERR_INVALID, "weights / grads struct missing or wrong size");
+  if (!tokens || !pos || !states || !grad_out) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
+  if (!w->bu_w1 || !w->bu_b1 || !w->bu_w2 || !w->td_w1 || !w->td_b1 || !w->td_w2)
+    return fail(GLOM_B200_ERR_INVALID, "a weight pointer is NULL");
+  if (!gr->d_tokens || !gr->d_pos || !gr->d_bu_w1 || !gr->d_bu_b1 || !gr->d_bu_w2 || !gr->d_bu_b2 || !gr->d_td_w1 ||
+      !gr->d_td_b1 || !gr->d_td_w2 || !gr->d_td_b2 || (!gr->d_state0 == !gr->d_init))
+    return fail(GLOM_B200_ERR_INVALID, "gradient pointers: all MLP/token/pos outputs and exactly one of d_state0 / d_init");
+  DeviceInfo di{};
+  if (int r = device_info(&di)) return r;
+  const Geometry g = make_geometry(cfg, batch);
+  const BackwardLayout wl = backward_layout(g);
+  if (!workspace || workspace_bytes < wl.total || reinterpret_cast<uintptr_t>(workspace) % 1024)
+    return fail(GLOM_B200_ERR_WORKSPACE, "backward workspace: need %zu bytes 1024-aligned, got %zu", wl.total, workspace_bytes);
+  BackwardArgs a{};
+  a.tokens = tokens; a.pos = pos; a.states = states; a.grad_out = grad_out;
+  a.bu_w1 = w->bu_w1; a.bu_b1 = w->bu_b1; a.bu_w2 = w->bu_w2; a.td_w1 = w->td_w1; a.td_b1 = w->td_b1; a.td_w2 = w->td_w2;
+  a.d_tokens = gr->d_tokens; a.d_pos = gr->d_pos; a.d_state0 = gr->d_state0; a.d_init = gr->d_init;
+  a.d_bu_w1 = gr->d_bu_w1; a.d_bu_b1 = gr->d_bu_b1; a.d_bu_w2 = gr->d_bu_w2; a.d_bu_b2 = gr->d_bu_b2;
+  a.d_td_w1 = gr->d_td_w1; a.d_td_b1 = gr->d_td_b1; a.d_td_w2 = gr->d_td_w2; a.d_td_b2 = gr->d_td_b2;
+  g_launches = 0;
+  cudaError_t e = backward_f32(g, a, iters, grad_all, workspace, static_cast<cudaStream_t>(stream), &g_launches);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "backward: %s", cudaGetErrorString(e));
+  g_err[0] = 0;
+  return 0;
+}
+
 GLOM_B200_API int glom_b200_profile_begin(void) {
   g_prof.enabled = true;
   g_prof.used = 0;

@@ -10,8 +10,10 @@ Mirrors the reference's public surface (glom_pytorch/glom_pytorch.py):
     ``iters=0`` returns S_0, output ``(B, n, L, d)`` or ``(T+1, B, n, L, d)`` fp32.
 
 What differs: the loop body (:131-145) plus GroupedFeedForward.forward / ConsensusAttention.forward is
-one call into ``libglom_b200.so`` (C ABI in include/glom_b200.h).  CUDA sm_100 only, forward only:
-there is no CPU / eager fallback -- inputs on other devices, or inputs that need autograd, raise.
+one call into ``libglom_b200.so`` (C ABI in include/glom_b200.h).  CUDA sm_100 only; there is no CPU / eager
+fallback -- inputs on other devices raise.  Under autograd the loop is a ``torch.autograd.Function`` whose backward
+is the engine's fp32 CUDA kernel set (``glom_b200_backward``): the forward keeps S_0..S_T and the reverse pass
+recomputes each step's intermediates (README.md:58-90 training use).
 
 Engine-only knob (keyword-only, additive): ``precision`` = ``"bf16"`` (default; tcgen05 tensor cores,
 bf16 operands, fp32 accumulate and fp32 state -- the arithmetic of the reference under
@@ -110,6 +112,49 @@ class ConsensusAttention(nn.Module):
         return side, self._mask_key[1]
 
 
+class _ColumnUpdate(torch.autograd.Function):
+    """The loop glom_pytorch.py:131-145 as one differentiable op: forward = glom_b200_forward (all states kept),
+    backward = glom_b200_backward (fp32, recompute per step)."""
+
+    @staticmethod
+    def forward(ctx, module, iters, return_all, tokens, pos, state0, init_levels, *weights):
+        tokens, pos = tokens.contiguous(), pos.contiguous()
+        states = module._run_engine(tokens, pos, state0, init_levels, iters, True)      # (T+1, B, n, L, d)
+        ctx.module, ctx.iters, ctx.return_all = module, iters, return_all
+        ctx.had_state0 = state0 is not None
+        ctx.save_for_backward(tokens, pos, states, *weights)
+        return states if return_all else states[iters]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module, iters = ctx.module, ctx.iters
+        tokens, pos, states, *weights = ctx.saved_tensors
+        device = states.device
+        b, n = tokens.shape[0], tokens.shape[1]
+        grad_out = grad_out.to(torch.float32).contiguous()
+        wts = [w.detach().to(torch.float32).contiguous() for w in weights]
+        zeros = torch.zeros
+        g = {"d_tokens": zeros_like32(tokens), "d_pos": zeros_like32(pos),
+             "d_state0": zeros(states.shape[1:], dtype=torch.float32, device=device) if ctx.had_state0 else None,
+             "d_init": None if ctx.had_state0 else zeros(module.levels, module.dim, dtype=torch.float32, device=device)}
+        names = ("d_bu_w1", "d_bu_b1", "d_bu_w2", "d_bu_b2", "d_td_w1", "d_td_b1", "d_td_w2", "d_td_b2")
+        for k, w in zip(names, wts):
+            g[k] = zeros_like32(w)
+        with torch.cuda.device(device):
+            cfg = module.engine_cfg(n, precision="fp32")
+            ws_bytes = _native.backward_workspace_bytes(cfg, b)
+            ws = _aligned_bytes(ws_bytes, device)
+            _native.backward(cfg, [w.data_ptr() for w in wts], tokens.data_ptr(), pos.data_ptr(), states.data_ptr(),
+                             grad_out.data_ptr(), {k: (None if v is None else v.data_ptr()) for k, v in g.items()},
+                             b, iters, ctx.return_all, ws.data_ptr(), ws.numel(),
+                             torch.cuda.current_stream(device).cuda_stream)
+        return (None, None, None, g["d_tokens"], g["d_pos"], g["d_state0"], g["d_init"], *[g[k] for k in names])
+
+
+def zeros_like32(t):
+    return torch.zeros(t.shape, dtype=torch.float32, device=t.device)
+
+
 class Glom(nn.Module):
     def __init__(self, *, dim=512, levels=6, image_size=224, patch_size=14, consensus_self=False,
                  local_consensus_radius=0, precision="bf16"):
@@ -166,9 +211,10 @@ class Glom(nn.Module):
             self._workspace = ws = _aligned_bytes(nbytes, device)
         return ws
 
-    def engine_cfg(self, n):
+    def engine_cfg(self, n, precision=None):
         side, d2 = self.attention.mask_params(n)
-        return _native.make_cfg(self.dim, self.levels, n, self.attention.attend_self, side, d2, self.precision)
+        return _native.make_cfg(self.dim, self.levels, n, self.attention.attend_self, side, d2,
+                                precision or self.precision)
 
     def tokens(self, img):
         """image_to_tokens (:114): fp32 CUDA-core kernel (precision fp32) or bf16 gather + tcgen05 GEMM (bf16)."""
@@ -192,32 +238,18 @@ class Glom(nn.Module):
         self._tok_launches = _native.last_launch_count()
         return out
 
-    # ------------------------------------------------------------------ the reference's forward (:110)
-    def forward(self, img, iters=None, levels=None, return_all=False):
-        if not img.is_cuda:
-            raise RuntimeError("glom_pytorch_b200.Glom runs on CUDA sm_100 only (no CPU fallback); "
-                               "move the module and inputs to a B200")
-        if torch.is_grad_enabled() and (img.requires_grad or (levels is not None and levels.requires_grad)
-                                        or any(p.requires_grad for p in self.parameters())):
-            raise RuntimeError("the B200 column-update engine is forward-only: call it under torch.no_grad() "
-                               "(or freeze the parameters); autograd through the loop is not implemented")
-        device = img.device
-        b = img.shape[0]
-        iters = self.levels * 2 if iters is None else int(iters)             # (:112)
+    # ------------------------------------------------------------------ engine call (no autograd)
+    def _run_engine(self, tokens, pos, state_in, init, iters, return_all):
+        """tokens (B,n,d), pos (n,d), state_in (B,n,L,d) or None, init (L,d): fp32 contiguous CUDA tensors."""
+        device = tokens.device
+        b, n = tokens.shape[0], tokens.shape[1]
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            tokens = self.tokens(img)                                        # (:114)
-            n = tokens.shape[1]
-            if n > self.pos_emb.num_embeddings:
-                raise IndexError(f"{n} patches exceed pos_emb size {self.pos_emb.num_embeddings}")   # (:117)
-            pos = self.pos_emb.weight.detach()[:n].float().contiguous()
-            state_in = None
-            if levels is not None:                                           # (:123)
-                if tuple(levels.shape) != (b, n, self.levels, self.dim):
-                    raise RuntimeError(f"levels must have shape {(b, n, self.levels, self.dim)}, "
-                                       f"got {tuple(levels.shape)}")
-                state_in = levels.detach().to(device=device, dtype=torch.float32).contiguous()
-            init = self.init_levels.detach().float().contiguous()
+            tokens = tokens.detach().to(torch.float32).contiguous()
+            pos = pos.detach().to(torch.float32).contiguous()
+            init = init.detach().to(torch.float32).contiguous()
+            if state_in is not None:
+                state_in = state_in.detach().to(device=device, dtype=torch.float32).contiguous()
             cfg = self.engine_cfg(n)
             packed = self._packed_weights(cfg, device, stream)
             shape = (b, n, self.levels, self.dim)
@@ -229,3 +261,32 @@ class Glom(nn.Module):
                             out.data_ptr(), b, iters, return_all, ws.data_ptr(), ws.numel(), stream)
             self.last_launches = _native.last_launch_count() + getattr(self, "_tok_launches", 0)
         return out
+
+    # ------------------------------------------------------------------ the reference's forward (:110)
+    def forward(self, img, iters=None, levels=None, return_all=False):
+        if not img.is_cuda:
+            raise RuntimeError("glom_pytorch_b200.Glom runs on CUDA sm_100 only (no CPU fallback); "
+                               "move the module and inputs to a B200")
+        b = img.shape[0]
+        iters = self.levels * 2 if iters is None else int(iters)             # (:112)
+        needs_grad = torch.is_grad_enabled() and (
+            img.requires_grad or (levels is not None and levels.requires_grad)
+            or any(p.requires_grad for p in self.parameters()))
+        p = self.patch_size
+        if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] % p or img.shape[3] % p:
+            raise RuntimeError(f"image {tuple(img.shape)} is not (B, 3, H, W) with H, W multiples of {p}")
+        n = (img.shape[2] // p) * (img.shape[3] // p)
+        if n > self.pos_emb.num_embeddings:
+            raise IndexError(f"{n} patches exceed pos_emb size {self.pos_emb.num_embeddings}")   # (:117)
+        if levels is not None and tuple(levels.shape) != (b, n, self.levels, self.dim):          # (:123)
+            raise RuntimeError(f"levels must have shape {(b, n, self.levels, self.dim)}, got {tuple(levels.shape)}")
+        if not needs_grad:
+            tokens = self.tokens(img)                                        # (:114) engine tokeniser
+            return self._run_engine(tokens, self.pos_emb.weight[:n], levels, self.init_levels, iters, return_all)
+        # training: tokeniser and parameter views stay in autograd (plain torch ops, once per call); the loop is the
+        # engine's differentiable op
+        self._tok_launches = 0
+        tokens = self.image_to_tokens[1](self.image_to_tokens[0](img.float()))                   # (:114)
+        pos = self.pos_emb.weight[:n]                                                            # (:117)
+        state0 = None if levels is None else levels.to(device=img.device, dtype=torch.float32)
+        return _ColumnUpdate.apply(self, iters, return_all, tokens, pos, state0, self.init_levels, *self._mlp_params())

@@ -132,6 +132,26 @@ GLOM_B200_API int glom_b200_last_launch_count(void);
 GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch, int iters, int return_all,
                                int which, size_t* out_offset, size_t* out_bytes);
 
+/* Backward of the column update: gradients of glom_b200_forward's loop
+ * (glom_pytorch.py:123-148) with respect to tokens, pos, the initial state (or init_levels) and the
+ * eight MLP tensors, given dL/d(output).  fp32 CUDA-core path; per-step intermediates are recomputed
+ * from the saved states.  All d_* buffers are ACCUMULATED into (zero them first); weights and their
+ * gradients use the reference's state_dict layout.
+ *   states    (iters+1, B, n, L, d) fp32: S_0..S_T as returned by forward(return_all=1)
+ *   grad_out  (iters+1, B, n, L, d) if grad_all else (B, n, L, d)
+ *   d_state0  (B, n, L, d) or NULL;  d_init (L, d) or NULL  (the one matching how the forward was started) */
+typedef struct glom_b200_grads {
+  uint32_t struct_size;
+  float* d_tokens; float* d_pos; float* d_state0; float* d_init;
+  float* d_bu_w1; float* d_bu_b1; float* d_bu_w2; float* d_bu_b2;
+  float* d_td_w1; float* d_td_b1; float* d_td_w2; float* d_td_b2;
+} glom_b200_grads;
+GLOM_B200_API int glom_b200_backward_workspace_bytes(const glom_b200_cfg* cfg, int batch, size_t* out_bytes);
+GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_weights_ref* weights,
+                       const float* tokens, const float* pos, const float* states, const float* grad_out,
+                       const glom_b200_grads* grads, int batch, int iters, int grad_all,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Per-kernel device timing for the roofline report (bench.py).  Between _begin and _end every
  * kernel the forward/tokenize calls of THIS thread enqueue is bracketed by CUDA events on the
  * launch stream (no synchronisation is added to the calls).  _end waits for those events and

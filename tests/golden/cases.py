@@ -46,3 +46,25 @@ def inputs(case, frame=0):
         levels = (rng.standard_normal((case["batch"], n, case["levels"], case["dim"]))
                   * case["levels_scale"]).astype(np.float32)
     return img, levels
+
+
+# ----------------------------------------------------------------------------- gradient fixtures (f2)
+GRAD_CASES = {
+    # BASELINE configs[0] shapes, default attention (diag fill), init_levels start, loss on every time step
+    "grad_c1_all": dict(dim=64, levels=3, image_size=28, patch_size=7, batch=2, iters=2, return_all=True,
+                        param_seed=11),
+    # carried-in levels (gradient w.r.t. the input state), radius mask + consensus_self, loss on the last step only
+    "grad_c1_masked": dict(dim=64, levels=3, image_size=28, patch_size=7, batch=2, iters=3, return_all=False,
+                           param_seed=12, consensus_self=True, local_consensus_radius=1.5, with_levels=True),
+}
+
+
+def grad_inputs(case):
+    rng = np.random.default_rng(2000 + case["param_seed"])
+    B, L, d = case["batch"], case["levels"], case["dim"]
+    n = (case["image_size"] // case["patch_size"]) ** 2
+    img = rng.standard_normal((B, 3, case["image_size"], case["image_size"])).astype(np.float32)
+    lv = rng.standard_normal((B, n, L, d)).astype(np.float32) if case.get("with_levels") else None
+    shape = ((case["iters"] + 1,) if case["return_all"] else ()) + (B, n, L, d)
+    cot = rng.standard_normal(shape).astype(np.float32)
+    return img, lv, cot

@@ -24,4 +24,4 @@ def model_kwargs(case):
                 local_consensus_radius=case.get("local_consensus_radius", 0))
 
 
-__all__ = ["CASES", "inputs", "load", "model_kwargs"]
+__all__ = ["CASES", "GOLDEN_DIR", "inputs", "load", "model_kwargs"]

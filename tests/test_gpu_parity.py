@@ -16,7 +16,7 @@ import torch
 
 import glom_pytorch_b200 as G
 from glom_pytorch_b200 import _native
-from golden_util import CASES, inputs, load, model_kwargs
+from golden_util import CASES, GOLDEN_DIR, inputs, load, model_kwargs
 from oracle import glom_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -302,7 +302,70 @@ def test_errors_are_reported_not_swallowed():
     x = torch.randn(1, 3, 28, 28, device=DEV)
     with torch.no_grad(), pytest.raises(RuntimeError, match="levels must have shape"):
         m(x, levels=torch.zeros(2, 16, 3, 64, device=DEV))
-    with pytest.raises(RuntimeError, match="forward-only"):
-        m(x)
+    out = m(x, iters=1)                     # under autograd the loop is a differentiable op (f2)
+    assert out.requires_grad and out.grad_fn is not None
     with torch.no_grad(), pytest.raises(IndexError):
         m(torch.randn(1, 3, 56, 56, device=DEV))
+
+
+# ----------------------------------------------------------------------------- backward
+from cases import GRAD_CASES, grad_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(GRAD_CASES))
+def test_gradients_match_reference_autograd(name, precision):
+    """loss = sum(out * cot): gradients of every parameter, of the image and of a carried-in state against the
+    reference's autograd (golden fixtures from tests/golden/make_golden_grads.py).
+    fp32 engine: max-abs <= 2e-4 * max(1, |ref|max) per tensor.  bf16 engine (bf16 forward, fp32 backward evaluated at
+    the bf16 forward's states): rel-Frobenius <= 3e-2 per tensor."""
+    import os
+    case = GRAD_CASES[name]
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        ref = {k: z[k] for k in z.files}
+    params = O.synth_params(case["dim"], case["levels"], case["image_size"], case["patch_size"], seed=case["param_seed"])
+    m = G.Glom(dim=case["dim"], levels=case["levels"], image_size=case["image_size"], patch_size=case["patch_size"],
+               consensus_self=case.get("consensus_self", False),
+               local_consensus_radius=case.get("local_consensus_radius", 0), precision=precision)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+    m = m.to(DEV)
+    img, lv, cot = grad_inputs(case)
+    img_t = torch.from_numpy(img).to(DEV).requires_grad_(True)
+    lv_t = None if lv is None else torch.from_numpy(lv).to(DEV).requires_grad_(True)
+    out = m(img_t, iters=case["iters"], levels=lv_t, return_all=case["return_all"])
+    (out * torch.from_numpy(cot).to(DEV)).sum().backward()
+    got = {"d_img": img_t.grad}
+    if lv_t is not None:
+        got["d_levels"] = lv_t.grad
+    for k, p in m.named_parameters():
+        got["d_" + k] = p.grad
+    for k, r in ref.items():
+        if k == "out":
+            continue
+        if got[k] is None:                      # unused parameter (e.g. init_levels when `levels` is given):
+            assert not r.any(), k               # the reference leaves .grad None there too (stored as zeros)
+            continue
+        gk = got[k].detach().cpu().numpy()
+        assert gk.shape == r.shape, (k, gk.shape, r.shape)
+        if precision == "fp32":
+            assert np.abs(gk - r).max() <= 2e-4 * max(1.0, np.abs(r).max()), (k, np.abs(gk - r).max())
+        else:
+            rel = np.linalg.norm(gk - r) / max(np.linalg.norm(r), 1e-30)
+            assert rel <= 3e-2, (k, rel)
+
+
+def test_readme_denoising_training_step_runs():
+    """README.md:58-90: loss on all_levels[7, :, :, -1], backward reaches every parameter."""
+    torch.manual_seed(0)
+    m = G.Glom(dim=64, levels=3, image_size=28, patch_size=7).to(DEV)
+    head = torch.nn.Linear(64, 7 * 7 * 3).to(DEV)
+    img = torch.randn(2, 3, 28, 28, device=DEV)
+    all_levels = m(img + torch.randn_like(img), return_all=True)
+    assert all_levels.shape == (7, 2, 16, 3, 64)
+    recon = head(all_levels[5, :, :, -1])
+    loss = torch.nn.functional.mse_loss(recon, torch.zeros_like(recon))
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        if k != "top_down.net.3.bias":
+            assert p.grad.abs().max() > 0, k
