@@ -251,6 +251,13 @@ __global__ void init_grad_kernel(int rows, int L, int d, const float* __restrict
   dinit[i] += acc;
 }
 
+__global__ void cast_bf16_rows(size_t n4, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
 static inline int nblk(size_t total, int block = 256) {
   const size_t want = (total + block - 1) / block;
   return (int)(want < (size_t)148 * 32 ? (want ? want : 1) : (size_t)148 * 32);
@@ -258,7 +265,7 @@ static inline int nblk(size_t total, int block = 256) {
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 #define CKL() do { if (launches) ++*launches; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
-BackwardLayout backward_layout(const Geometry& g) {
+BackwardLayout backward_layout(const Geometry& g, int precision) {
   BackwardLayout w{};
   const size_t state = (size_t)g.rows * g.L * g.d * 4, hid = (size_t)g.rows * 4 * g.d * 4;
   const size_t attn = (size_t)g.B * g.L * g.n * g.n * 4;
@@ -270,6 +277,20 @@ BackwardLayout backward_layout(const Geometry& g) {
   w.pre_off = take(hid); w.h_off = take(hid); w.dh_off = take(hid);
   w.xp_off = take((size_t)g.rows * g.d * 4); w.dx_off = take((size_t)g.rows * g.d * 4);
   w.attn_off = take(attn); w.dattn_off = take(attn);
+  if (precision == 1 && g.d % 256 == 0) {     // tensor-core MLP backward
+    const size_t m128 = (g.rows + 127) / 128;
+    w.blocked_bytes = (size_t)g.G * m128 * 128 * 4 * g.d * 2;
+    w.xb_off = take((size_t)g.rows * g.d * 2);
+    w.sb_off = take((size_t)g.rows * g.L * g.d * 2);
+    w.sp_off = take((size_t)g.rows * (g.L - 1) * g.d * 2);
+    w.gsb_off = take((size_t)g.rows * g.L * g.d * 2);
+    w.w1p_off = take((size_t)g.G * 4 * g.d * g.d * 2);
+    w.w2t_off = take((size_t)g.G * 4 * g.d * g.d * 2);
+    w.w1t_off = take((size_t)g.G * 4 * g.d * g.d * 2);
+    w.b1p_off = take((size_t)g.G * 4 * g.d * 4);
+    w.bpre_off = take(w.blocked_bytes); w.bh_off = take(w.blocked_bytes); w.bdpre_off = take(w.blocked_bytes);
+    w.dxall_off = take((size_t)g.rows * g.G * g.d * 4);
+  }
   w.total = off;
   return w;
 }
@@ -277,7 +298,7 @@ BackwardLayout backward_layout(const Geometry& g) {
 // One reverse step: given gin = dL/dS_{t+1}, produce ds = dL/dS_t (without the external grad of slab t) and
 // accumulate parameter / token / pos gradients.
 static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const float* s_t, const float* gin,
-                                 char* ws, const BackwardLayout& wl, cudaStream_t st, int* launches) {
+                                 char* ws, const BackwardLayout& wl, bool mlp_on_tc, cudaStream_t st, int* launches) {
   const int R = g.rows, L = g.L, d = g.d, n = g.n, h4 = 4 * g.d;
   const long long ld = (long long)L * d;
   float* gs = reinterpret_cast<float*>(ws + wl.gs_off);       // gin / c
@@ -291,8 +312,8 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
   scale_by_contrib_kernel<<<nblk(state), 256, 0, st>>>(state, L, d, gin, gs, ds);
   CKL();
 
-  // ---- the two grouped MLPs (:23-36), one group at a time
-  for (int net = 0; net < 2; ++net) {
+  // ---- the two grouped MLPs (:23-36), one group at a time (fp32 path; the bf16 engine runs them on tensor cores)
+  for (int net = 0; net < 2 && !mlp_on_tc; ++net) {
     const int groups = net == 0 ? L : L - 1;
     const float* w1 = net == 0 ? a.bu_w1 : a.td_w1;
     const float* b1 = net == 0 ? a.bu_b1 : a.td_b1;
@@ -390,33 +411,182 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
   return cudaSuccess;
 }
 
-cudaError_t backward_f32(const Geometry& g, const BackwardArgs& a, int iters, int grad_all, void* workspace,
-                         cudaStream_t st, int* launches) {
-  const BackwardLayout wl = backward_layout(g);
+// =====================================================================================
+// helpers of the tensor-core MLP backward
+// =====================================================================================
+// bf16 packs of the current weights: W1p (G*4d, d), W2T (G*4d, d) = W2^T, W1T (G*d, 4d) = W1^T, b1p (G*4d); groups
+// interleaved bu_0, td_0, bu_1, ...
+__global__ void pack_bwd_weights_kernel(int d, int L, const float* __restrict__ bu_w1, const float* __restrict__ bu_b1,
+                                        const float* __restrict__ bu_w2, const float* __restrict__ td_w1,
+                                        const float* __restrict__ td_b1, const float* __restrict__ td_w2,
+                                        __nv_bfloat16* __restrict__ w1p, __nv_bfloat16* __restrict__ w2t,
+                                        __nv_bfloat16* __restrict__ w1t, float* __restrict__ b1p) {
+  const int G = 2 * L - 1, h = 4 * d;
+  const size_t nw = (size_t)G * h * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw + (size_t)G * h; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nw) {
+      const int g = (int)(i / ((size_t)h * d)), l = g >> 1;
+      const size_t q = i % ((size_t)h * d);
+      const int j = (int)(q / d), c = (int)(q % d);                 // element (j, c) of W1_g (4d x d)
+      const float* W1 = ((g & 1) ? td_w1 : bu_w1) + (size_t)l * h * d;
+      const float* W2 = ((g & 1) ? td_w2 : bu_w2) + (size_t)l * d * h;
+      const float v1 = W1[(size_t)j * d + c];
+      w1p[i] = __float2bfloat16_rn(v1);                             // (g*4d + j, c)
+      w1t[((size_t)g * d + c) * h + j] = __float2bfloat16_rn(v1);   // (g*d + c, j)
+      w2t[i] = __float2bfloat16_rn(W2[(size_t)c * h + j]);          // (g*4d + j, o = c)  <- W2[o][j]
+    } else {
+      const size_t q = i - nw;
+      const int g = (int)(q / h), l = g >> 1, j = (int)(q % h);
+      b1p[q] = ((g & 1) ? td_b1 : bu_b1)[(size_t)l * h + j];
+    }
+  }
+}
+// bf16 shadows of a step: sb = bf16(S_t), sp = bf16(S_t[:, 1:] + pos), gsb = bf16(gs)
+__global__ void bwd_shadows_kernel(int rows, int n, int L, int d, const float* __restrict__ s, const float* __restrict__ gs,
+                                   const float* __restrict__ pos, __nv_bfloat16* __restrict__ sb,
+                                   __nv_bfloat16* __restrict__ sp, __nv_bfloat16* __restrict__ gsb) {
+  const size_t total4 = (size_t)rows * L * d / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int c = (int)(e % d), l = (int)((e / d) % L);
+    const size_t r = e / ((size_t)L * d);
+    const float4 v = *reinterpret_cast<const float4*>(s + e);
+    const float4 gv = *reinterpret_cast<const float4*>(gs + e);
+    *reinterpret_cast<uint2*>(sb + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(gsb + e) = make_uint2(pack_bf16x2(gv.x, gv.y), pack_bf16x2(gv.z, gv.w));
+    if (l >= 1) {
+      const float4 q = *reinterpret_cast<const float4*>(pos + (size_t)(r % n) * d + c);
+      *reinterpret_cast<uint2*>(sp + (r * (L - 1) + (l - 1)) * d + c) =
+          make_uint2(pack_bf16x2(v.x + q.x, v.y + q.y), pack_bf16x2(v.z + q.z, v.w + q.w));
+    }
+  }
+}
+// scatter of dx (R, G, d): bottom-up group l -> level l-1 (tokens for l = 0), top-down group l -> level l+1
+__global__ void scatter_dx_kernel(int rows, int L, int d, const float* __restrict__ dx, float* __restrict__ ds,
+                                  float* __restrict__ d_tokens) {
+  const int G = 2 * L - 1;
+  const size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / d;
+    const int c = (int)(i % d);
+    const float* src = dx + r * G * d + c;
+    d_tokens[i] += src[0];
+    for (int l = 1; l < L; ++l) ds[(r * L + l - 1) * d + c] += src[(size_t)(2 * l) * d];
+    for (int l = 0; l < L - 1; ++l) ds[(r * L + l + 1) * d + c] += src[(size_t)(2 * l + 1) * d];
+  }
+}
+// d_pos[nn, c] += sum over images and top-down groups of dx
+__global__ void pos_grad_all_kernel(int B, int n, int L, int d, const float* __restrict__ dx, float* __restrict__ dpos) {
+  const int G = 2 * L - 1;
+  const size_t total = (size_t)n * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t nn = i / d;
+    const int c = (int)(i % d);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+      for (int l = 0; l < L - 1; ++l) acc += dx[(((size_t)b * n + nn) * G + 2 * l + 1) * d + c];
+    dpos[i] += acc;
+  }
+}
+// first-layer bias gradients: column sums of the blocked bf16 dpre (G, m128, 4d/64, 128, 64)
+__global__ void colsum_blocked_kernel(int rows, int m128, int d, int L, const __nv_bfloat16* __restrict__ dpre,
+                                      float* __restrict__ d_bu_b1, float* __restrict__ d_td_b1) {
+  const int h = 4 * d, kbg = h / 64;
+  const int g = blockIdx.y, cb = blockIdx.x;            // group, 64-column block
+  const int col = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 row slices
+  __shared__ float red[4][64];
+  float acc = 0.f;
+  for (int r = part; r < rows; r += 4) {
+    const size_t off = ((size_t)((g * m128 + (r >> 7)) * kbg + cb) * 128 + (r & 127)) * 64 + col;
+    acc += __bfloat162float(dpre[off]);
+  }
+  red[part][col] = acc;
+  __syncthreads();
+  if (part == 0) {
+    const float s = red[0][col] + red[1][col] + red[2][col] + red[3][col];
+    float* dst = (g & 1) ? d_td_b1 : d_bu_b1;
+    dst[(size_t)(g >> 1) * h + cb * 64 + col] += s;
+  }
+}
+
+int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int iters, int grad_all, void* workspace,
+                 EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen) {
+#define CKI(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, errlen, "backward: %s", cudaGetErrorString(e_)); return -3; } } while (0)
+#define CKLI() do { if (launches) ++*launches; CKI(cudaGetLastError()); } while (0)
+  const BackwardLayout wl = backward_layout(g, precision);
+  const bool tc = precision == 1 && g.d % 256 == 0;
   char* ws = static_cast<char*>(workspace);
   const size_t state = (size_t)g.rows * g.L * g.d;
   float* G = reinterpret_cast<float*>(ws + wl.g_off);
+  float* gs = reinterpret_cast<float*>(ws + wl.gs_off);
   float* ds = reinterpret_cast<float*>(ws + wl.ds_off);
-  // G = dL/dS_T
+  MlpBwdTc m{};
+  if (tc) {
+    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
+    m.xb = xb;
+    m.sb = reinterpret_cast<__nv_bfloat16*>(ws + wl.sb_off);
+    m.sp = reinterpret_cast<__nv_bfloat16*>(ws + wl.sp_off);
+    m.gsb = reinterpret_cast<__nv_bfloat16*>(ws + wl.gsb_off);
+    m.w1p = reinterpret_cast<__nv_bfloat16*>(ws + wl.w1p_off);
+    m.w2t = reinterpret_cast<__nv_bfloat16*>(ws + wl.w2t_off);
+    m.w1t = reinterpret_cast<__nv_bfloat16*>(ws + wl.w1t_off);
+    m.b1p = reinterpret_cast<float*>(ws + wl.b1p_off);
+    m.pre = reinterpret_cast<__nv_bfloat16*>(ws + wl.bpre_off);
+    m.h = reinterpret_cast<__nv_bfloat16*>(ws + wl.bh_off);
+    m.dpre = reinterpret_cast<__nv_bfloat16*>(ws + wl.bdpre_off);
+    m.dx = reinterpret_cast<float*>(ws + wl.dxall_off);
+    m.d_bu_w1 = a.d_bu_w1; m.d_bu_w2 = a.d_bu_w2; m.d_td_w1 = a.d_td_w1; m.d_td_w2 = a.d_td_w2;
+    pack_bwd_weights_kernel<<<148 * 8, 256, 0, st>>>(g.d, g.L, a.bu_w1, a.bu_b1, a.bu_w2, a.td_w1, a.td_b1, a.td_w2,
+                                                     const_cast<__nv_bfloat16*>(m.w1p), const_cast<__nv_bfloat16*>(m.w2t),
+                                                     const_cast<__nv_bfloat16*>(m.w1t), const_cast<float*>(m.b1p));
+    CKLI();
+    const size_t n4 = (size_t)g.rows * g.d / 4;
+    cast_bf16_rows<<<nblk(n4), 256, 0, st>>>(n4, a.tokens, xb);
+    CKLI();
+    if (g.rows % 128) {     // rows of the last 128-row block beyond R are read as K entries of the dW GEMMs: keep them zero
+      CKI(cudaMemsetAsync(m.h, 0, wl.blocked_bytes, st));
+      CKI(cudaMemsetAsync(m.dpre, 0, wl.blocked_bytes, st));
+    }
+  }
   const float* top = grad_all ? a.grad_out + (size_t)iters * state : a.grad_out;
-  CK(cudaMemcpyAsync(G, top, state * 4, cudaMemcpyDeviceToDevice, st));
+  CKI(cudaMemcpyAsync(G, top, state * 4, cudaMemcpyDeviceToDevice, st));
   for (int t = iters - 1; t >= 0; --t) {
-    CK(backward_step(g, a, a.states + (size_t)t * state, G, ws, wl, st, launches));
-    CK(cudaMemcpyAsync(G, ds, state * 4, cudaMemcpyDeviceToDevice, st));
+    const float* s_t = a.states + (size_t)t * state;
+    CKI(backward_step(g, a, s_t, G, ws, wl, tc, st, launches));       // scale, (fp32 MLPs), attention -> ds
+    if (tc) {
+      bwd_shadows_kernel<<<nblk(state / 4), 256, 0, st>>>(g.rows, g.n, g.L, g.d, s_t, gs, a.pos,
+                                                          const_cast<__nv_bfloat16*>(m.sb), const_cast<__nv_bfloat16*>(m.sp),
+                                                          const_cast<__nv_bfloat16*>(m.gsb));
+      CKLI();
+      if (int r = mlp_backward_tc(g, m, enc, num_sms, st, launches, err, errlen)) return r;
+      scatter_dx_kernel<<<nblk((size_t)g.rows * g.d), 256, 0, st>>>(g.rows, g.L, g.d, m.dx, ds, a.d_tokens);
+      CKLI();
+      pos_grad_all_kernel<<<nblk((size_t)g.n * g.d), 256, 0, st>>>(g.B, g.n, g.L, g.d, m.dx, a.d_pos);
+      CKLI();
+      colsum_acc_kernel<<<(g.L * g.d + 31) / 32, 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2);
+      CKLI();
+      colsum_acc_kernel<<<((g.L - 1) * g.d + 31) / 32, 256, 0, st>>>(g.rows, (g.L - 1) * g.d, (long long)g.L * g.d, gs, a.d_td_b2);
+      CKLI();
+      colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
+      CKLI();
+    }
+    CKI(cudaMemcpyAsync(G, ds, state * 4, cudaMemcpyDeviceToDevice, st));
     if (grad_all) {
       add_kernel<<<nblk(state), 256, 0, st>>>(state, a.grad_out + (size_t)t * state, G);
-      CKL();
+      CKLI();
     }
   }
   if (a.d_state0) {
     add_kernel<<<nblk(state), 256, 0, st>>>(state, G, a.d_state0);
-    CKL();
+    CKLI();
   }
   if (a.d_init) {
     init_grad_kernel<<<(g.L * g.d + 255) / 256, 256, 0, st>>>(g.rows, g.L, g.d, G, a.d_init);
-    CKL();
+    CKLI();
   }
-  return cudaSuccess;
+  return 0;
+#undef CKI
+#undef CKLI
 }
 
 }  // namespace glom

@@ -123,18 +123,34 @@ struct BackwardArgs {
   const float* pos;      // (n, d)
   const float* states;   // (T+1, R, L, d): S_0 .. S_T of the forward
   const float* grad_out; // (T+1, R, L, d) if grad_all else (R, L, d): dL/d(returned tensor)
-  const float *bu_w1, *bu_b1, *bu_w2, *td_w1, *td_b1, *td_w2;   // reference layout, fp32
+  const float *bu_w1, *bu_b1, *bu_w2, *td_w1, *td_b1, *td_w2;   // reference layout, fp32 (second biases are not needed)
   // outputs, ACCUMULATED into (caller zero-initialises); d_state0 / d_init: exactly one is non-NULL
   float *d_tokens, *d_pos, *d_state0, *d_init;
   float *d_bu_w1, *d_bu_b1, *d_bu_w2, *d_bu_b2, *d_td_w1, *d_td_b1, *d_td_w2, *d_td_b2;
 };
 struct BackwardLayout {
   size_t g_off, gs_off, ds_off, khat_off, dkhat_off, rnorm_off, pre_off, h_off, dh_off, xp_off, dx_off, attn_off,
-      dattn_off, total;
+      dattn_off;
+  // bf16 (tensor-core) MLP backward only
+  size_t xb_off, sb_off, sp_off, gsb_off, w1p_off, w2t_off, w1t_off, b1p_off, bpre_off, bh_off, bdpre_off, dxall_off;
+  size_t blocked_bytes;
+  size_t total;
 };
-BackwardLayout backward_layout(const Geometry& g);
-cudaError_t backward_f32(const Geometry& g, const BackwardArgs& a, int iters, int grad_all, void* workspace,
-                         cudaStream_t st, int* launches);
+// tensor-core MLP backward (tc_bwd_kernels.cu)
+struct MlpBwdTc {
+  const __nv_bfloat16 *xb, *sb, *sp, *gsb;      // bf16 shadows: tokens, S_t, S_t[:,1:]+pos, dL/dS_{t+1}/c
+  const __nv_bfloat16 *w1p, *w2t, *w1t;        // (G*4d, d), (G*4d, d) = W2^T, (G*d, 4d) = W1^T, groups interleaved bu/td
+  const float* b1p;                            // (G*4d)
+  __nv_bfloat16 *pre, *h, *dpre;               // blocked (G, R_pad/128, 4d/64, 128, 64)
+  float* dx;                                   // (R, G, d)
+  float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
+};
+int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
+                    char* err, size_t errlen);
+
+BackwardLayout backward_layout(const Geometry& g, int precision);
+int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int iters, int grad_all, void* workspace,
+                 EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and per function: remember, per device, the
 // largest size already configured for one kernel (one instance of this per kernel template instantiation).

@@ -310,7 +310,7 @@ GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, cons
 GLOM_B200_API int glom_b200_backward_workspace_bytes(const glom_b200_cfg* cfg, int batch, size_t* out_bytes) {
   if (int r = check_cfg(cfg)) return r;
   if (batch < 1 || !out_bytes) return fail(GLOM_B200_ERR_INVALID, "bad batch/out_bytes");
-  *out_bytes = backward_layout(make_geometry(cfg, batch)).total;
+  *out_bytes = backward_layout(make_geometry(cfg, batch), cfg->precision).total;
   return 0;
 }
 
@@ -331,7 +331,7 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
   DeviceInfo di{};
   if (int r = device_info(&di)) return r;
   const Geometry g = make_geometry(cfg, batch);
-  const BackwardLayout wl = backward_layout(g);
+  const BackwardLayout wl = backward_layout(g, cfg->precision);
   if (!workspace || workspace_bytes < wl.total || reinterpret_cast<uintptr_t>(workspace) % 1024)
     return fail(GLOM_B200_ERR_WORKSPACE, "backward workspace: need %zu bytes 1024-aligned, got %zu", wl.total, workspace_bytes);
   BackwardArgs a{};
@@ -341,8 +341,10 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
   a.d_bu_w1 = gr->d_bu_w1; a.d_bu_b1 = gr->d_bu_b1; a.d_bu_w2 = gr->d_bu_w2; a.d_bu_b2 = gr->d_bu_b2;
   a.d_td_w1 = gr->d_td_w1; a.d_td_b1 = gr->d_td_b1; a.d_td_w2 = gr->d_td_w2; a.d_td_b2 = gr->d_td_b2;
   g_launches = 0;
-  cudaError_t e = backward_f32(g, a, iters, grad_all, workspace, static_cast<cudaStream_t>(stream), &g_launches);
-  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "backward: %s", cudaGetErrorString(e));
+  char msg[400] = "";
+  if (int r = backward_run(g, a, cfg->precision, iters, grad_all, workspace, g_encode, di.sms,
+                           static_cast<cudaStream_t>(stream), &g_launches, msg, sizeof(msg)))
+    return fail(r == -1 ? GLOM_B200_ERR_INVALID : GLOM_B200_ERR_CUDA, "%s", msg);
   g_err[0] = 0;
   return 0;
 }

@@ -141,7 +141,7 @@ class _ColumnUpdate(torch.autograd.Function):
         for k, w in zip(names, wts):
             g[k] = zeros_like32(w)
         with torch.cuda.device(device):
-            cfg = module.engine_cfg(n, precision="fp32")
+            cfg = module.engine_cfg(n)           # bf16 engine: MLP GEMMs of the backward on tensor cores
             ws_bytes = _native.backward_workspace_bytes(cfg, b)
             ws = _aligned_bytes(ws_bytes, device)
             _native.backward(cfg, [w.data_ptr() for w in wts], tokens.data_ptr(), pos.data_ptr(), states.data_ptr(),
