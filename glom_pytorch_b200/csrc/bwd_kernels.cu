@@ -167,7 +167,7 @@ __global__ void add_kernel(size_t total, const float* __restrict__ src, float* _
 }
 // khat = S / max(|S|, 1e-12) per (row, level) ; rnorm = 1 / max(|S|, 1e-12)      (F.normalize, :58)
 __global__ void normalize_rows_kernel(int nrows, int d, const float* __restrict__ s, float* __restrict__ khat,
-                                      float* __restrict__ rnorm) {
+                                      float* __restrict__ rnorm, __nv_bfloat16* __restrict__ khat_b) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= nrows) return;
   const float* p = s + (size_t)row * d;
@@ -176,19 +176,23 @@ __global__ void normalize_rows_kernel(int nrows, int d, const float* __restrict_
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float r = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-  for (int c = lane; c < d; c += 32) khat[(size_t)row * d + c] = p[c] * r;
+  for (int c = lane; c < d; c += 32) {
+    const float v = p[c] * r;
+    khat[(size_t)row * d + c] = v;
+    if (khat_b) khat_b[(size_t)row * d + c] = __float2bfloat16_rn(v);
+  }
   if (lane == 0) rnorm[row] = r;
 }
 // in-place masked softmax over the last dim of sim (Z, n, n)     (:62-71); one warp per row
-__global__ void attn_softmax_kernel(int Z, int n, int attend_self, int mask_side, int mask_d2_max,
-                                    float* __restrict__ sim) {
+__global__ void attn_softmax_kernel(int Z, int n, int attend_self, int mask_side, int mask_d2_max, float scale,
+                                    float* __restrict__ sim, __nv_bfloat16* __restrict__ a_b) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Z * n) return;
   const int i = row % n;
   float* p = sim + (size_t)row * n;
   float m = -3.402823466e+38f;
   for (int j = lane; j < n; j += 32) {
-    float v = p[j];
+    float v = p[j] * scale;
     if (!attend_self && j == i) v = -5e-4f;
     if (mask_side > 0) {
       const int dh = i / mask_side - j / mask_side, dw = i % mask_side - j % mask_side;
@@ -204,11 +208,16 @@ __global__ void attn_softmax_kernel(int Z, int n, int attend_self, int mask_side
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.0f / sum;
-  for (int j = lane; j < n; j += 32) p[j] *= inv;
+  for (int j = lane; j < n; j += 32) {
+    const float a = p[j] * inv;
+    p[j] = a;
+    if (a_b) a_b[(size_t)row * n + j] = __float2bfloat16_rn(a);
+  }
 }
 // dsim = A * (dA - sum_j A dA), zero where the logit was a constant (diagonal fill, radius mask); in place on dA
 __global__ void attn_softmax_bwd_kernel(int Z, int n, int attend_self, int mask_side, int mask_d2_max,
-                                        const float* __restrict__ A, float* __restrict__ dA) {
+                                        const float* __restrict__ A, float* __restrict__ dA, float scale,
+                                        __nv_bfloat16* __restrict__ dsim_b) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= Z * n) return;
   const int i = row % n;
@@ -226,6 +235,7 @@ __global__ void attn_softmax_bwd_kernel(int Z, int n, int attend_self, int mask_
       if (dh * dh + dw * dw > mask_d2_max) v = 0.f;
     }
     g[j] = v;
+    if (dsim_b) dsim_b[(size_t)row * n + j] = __float2bfloat16_rn(v * scale);
   }
 }
 // ds[row] += (dkhat - khat (khat . dkhat)) * rnorm        (backward of F.normalize); one warp per (row, level)
@@ -290,6 +300,9 @@ BackwardLayout backward_layout(const Geometry& g, int precision) {
     w.b1p_off = take((size_t)g.G * 4 * g.d * 4);
     w.bpre_off = take(w.blocked_bytes); w.bh_off = take(w.blocked_bytes); w.bdpre_off = take(w.blocked_bytes);
     w.dxall_off = take((size_t)g.rows * g.G * g.d * 4);
+    w.khatb_off = take((size_t)g.rows * g.L * g.d * 2);
+    w.ab_off = take((size_t)g.B * g.L * g.n * g.n * 2);
+    w.dsimb_off = take((size_t)g.B * g.L * g.n * g.n * 2);
   }
   w.total = off;
   return w;
@@ -298,7 +311,8 @@ BackwardLayout backward_layout(const Geometry& g, int precision) {
 // One reverse step: given gin = dL/dS_{t+1}, produce ds = dL/dS_t (without the external grad of slab t) and
 // accumulate parameter / token / pos gradients.
 static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const float* s_t, const float* gin,
-                                 char* ws, const BackwardLayout& wl, bool mlp_on_tc, cudaStream_t st, int* launches) {
+                                 char* ws, const BackwardLayout& wl, bool mlp_on_tc, bool attn_on_tc, cudaStream_t st,
+                                 int* launches) {
   const int R = g.rows, L = g.L, d = g.d, n = g.n, h4 = 4 * g.d;
   const long long ld = (long long)L * d;
   float* gs = reinterpret_cast<float*>(ws + wl.gs_off);       // gin / c
@@ -372,8 +386,8 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
     }
   }
 
-  // ---- consensus attention (:56-73), all (image, level) problems batched
-  {
+  // ---- consensus attention (:56-73), all (image, level) problems batched (fp32 path)
+  if (!attn_on_tc) {
     float* khat = reinterpret_cast<float*>(ws + wl.khat_off);
     float* dkhat = reinterpret_cast<float*>(ws + wl.dkhat_off);
     float* rnorm = reinterpret_cast<float*>(ws + wl.rnorm_off);
@@ -383,13 +397,13 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
     const long long sb = (long long)n * ld, sl = d, nn = (long long)n * n;
     const float scale = 1.0f / sqrtf((float)d);
     const int wblocks = (R * L * 32 + 255) / 256;
-    normalize_rows_kernel<<<wblocks, 256, 0, st>>>(R * L, d, s_t, khat, rnorm);
+    normalize_rows_kernel<<<wblocks, 256, 0, st>>>(R * L, d, s_t, khat, rnorm, nullptr);
     CKL();
     GemmF32 q{};
     // sim = scale * Q Khat^T                              (n x n per (b, l))
-    q = GemmF32{n, n, d, L, Mat{s_t, ld, 1, sb, sl}, Mat{khat, 1, ld, sb, sl}, MatOut{A, n, 1, nn * L, nn}, scale, 0.f, nullptr};
+    q = GemmF32{n, n, d, L, Mat{s_t, ld, 1, sb, sl}, Mat{khat, 1, ld, sb, sl}, MatOut{A, n, 1, nn * L, nn}, 1.f, 0.f, nullptr};
     CK(gemm_f32(q, Z, st, launches));
-    attn_softmax_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A);
+    attn_softmax_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, scale, A, nullptr);
     CKL();
     // dA = dC V^T
     q = GemmF32{n, n, d, L, Mat{gs, ld, 1, sb, sl}, Mat{s_t, 1, ld, sb, sl}, MatOut{dA, n, 1, nn * L, nn}, 1.f, 0.f, nullptr};
@@ -397,7 +411,7 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
     // dV: ds += A^T dC
     q = GemmF32{n, d, n, L, Mat{A, 1, n, nn * L, nn}, Mat{gs, ld, 1, sb, sl}, MatOut{ds, ld, 1, sb, sl}, 1.f, 1.f, nullptr};
     CK(gemm_f32(q, Z, st, launches));
-    attn_softmax_bwd_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A, dA);
+    attn_softmax_bwd_kernel<<<(Z * n * 32 + 255) / 256, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A, dA, 1.f, nullptr);
     CKL();
     // dQ: ds += scale * dsim Khat
     q = GemmF32{n, d, n, L, Mat{dA, n, 1, nn * L, nn}, Mat{khat, ld, 1, sb, sl}, MatOut{ds, ld, 1, sb, sl}, scale, 1.f, nullptr};
@@ -515,6 +529,7 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
 #define CKLI() do { if (launches) ++*launches; CKI(cudaGetLastError()); } while (0)
   const BackwardLayout wl = backward_layout(g, precision);
   const bool tc = precision == 1 && g.d % 256 == 0;
+  const bool attn_tc = tc && g.n % 8 == 0;      // TMA row pitch of the (Z, n, n) bf16 buffers must be a multiple of 16 B
   char* ws = static_cast<char*>(workspace);
   const size_t state = (size_t)g.rows * g.L * g.d;
   float* G = reinterpret_cast<float*>(ws + wl.g_off);
@@ -552,12 +567,41 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
   CKI(cudaMemcpyAsync(G, top, state * 4, cudaMemcpyDeviceToDevice, st));
   for (int t = iters - 1; t >= 0; --t) {
     const float* s_t = a.states + (size_t)t * state;
-    CKI(backward_step(g, a, s_t, G, ws, wl, tc, st, launches));       // scale, (fp32 MLPs), attention -> ds
+    CKI(backward_step(g, a, s_t, G, ws, wl, tc, attn_tc, st, launches));   // scale (+ the fp32 MLP / attention backward)
     if (tc) {
       bwd_shadows_kernel<<<nblk(state / 4), 256, 0, st>>>(g.rows, g.n, g.L, g.d, s_t, gs, a.pos,
                                                           const_cast<__nv_bfloat16*>(m.sb), const_cast<__nv_bfloat16*>(m.sp),
                                                           const_cast<__nv_bfloat16*>(m.gsb));
       CKLI();
+      // ---- consensus attention backward: the five (n x n x d) GEMM families on tensor cores, softmax in fp32
+      if (attn_tc) {
+        float* khat = reinterpret_cast<float*>(ws + wl.khat_off);
+        float* dkhat = reinterpret_cast<float*>(ws + wl.dkhat_off);
+        float* rnorm = reinterpret_cast<float*>(ws + wl.rnorm_off);
+        float* A = reinterpret_cast<float*>(ws + wl.attn_off);
+        float* dA = reinterpret_cast<float*>(ws + wl.dattn_off);
+        __nv_bfloat16* khat_b = reinterpret_cast<__nv_bfloat16*>(ws + wl.khatb_off);
+        __nv_bfloat16* a_b = reinterpret_cast<__nv_bfloat16*>(ws + wl.ab_off);
+        __nv_bfloat16* dsim_b = reinterpret_cast<__nv_bfloat16*>(ws + wl.dsimb_off);
+        const int Z = g.B * g.L, n = g.n, d = g.d;
+        const float scale = 1.0f / sqrtf((float)d);
+        const int wblocks = (g.rows * g.L * 32 + 255) / 256, rblocks = (Z * n * 32 + 255) / 256;
+        normalize_rows_kernel<<<wblocks, 256, 0, st>>>(g.rows * g.L, d, s_t, khat, rnorm, khat_b);
+        CKLI();
+        // logits = Q Khat^T (scaled inside the softmax), dA = dC V^T
+        if (int r = attn_bwd_gemm_tc(g, m.sb, 1, 0, khat_b, 1, 0, n, d, 0, A, enc, num_sms, st, launches, err, errlen)) return r;
+        attn_softmax_kernel<<<rblocks, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, scale, A, a_b);
+        CKLI();
+        if (int r = attn_bwd_gemm_tc(g, m.gsb, 1, 0, m.sb, 1, 0, n, d, 0, dA, enc, num_sms, st, launches, err, errlen)) return r;
+        attn_softmax_bwd_kernel<<<rblocks, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A, dA, scale, dsim_b);
+        CKLI();
+        // dV: ds += A^T dC ;  dQ: ds += (scale dsim) Khat ;  dKhat = (scale dsim)^T Q
+        if (int r = attn_bwd_gemm_tc(g, a_b, 0, 1, m.gsb, 1, 1, d, n, 1, ds, enc, num_sms, st, launches, err, errlen)) return r;
+        if (int r = attn_bwd_gemm_tc(g, dsim_b, 0, 0, khat_b, 1, 1, d, n, 1, ds, enc, num_sms, st, launches, err, errlen)) return r;
+        if (int r = attn_bwd_gemm_tc(g, dsim_b, 0, 1, m.sb, 1, 1, d, n, 2, dkhat, enc, num_sms, st, launches, err, errlen)) return r;
+        normalize_bwd_kernel<<<wblocks, 256, 0, st>>>(g.rows * g.L, d, khat, dkhat, rnorm, ds);
+        CKLI();
+      }
       if (int r = mlp_backward_tc(g, m, enc, num_sms, st, launches, err, errlen)) return r;
       scatter_dx_kernel<<<nblk((size_t)g.rows * g.d), 256, 0, st>>>(g.rows, g.L, g.d, m.dx, ds, a.d_tokens);
       CKLI();

@@ -133,6 +133,7 @@ struct BackwardLayout {
       dattn_off;
   // bf16 (tensor-core) MLP backward only
   size_t xb_off, sb_off, sp_off, gsb_off, w1p_off, w2t_off, w1t_off, b1p_off, bpre_off, bh_off, bdpre_off, dxall_off;
+  size_t khatb_off, ab_off, dsimb_off;     // bf16 khat (state-like), probabilities and scaled dsim (Z, n, n)
   size_t blocked_bytes;
   size_t total;
 };
@@ -147,6 +148,10 @@ struct MlpBwdTc {
 };
 int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
                     char* err, size_t errlen);
+
+int attn_bwd_gemm_tc(const Geometry& g, const void* a_src, int a_state, int a_mn, const void* b_src, int b_state, int b_mn,
+                     int N, int K, int out_kind, float* out, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
+                     char* err, size_t errlen);
 
 BackwardLayout backward_layout(const Geometry& g, int precision);
 int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int iters, int grad_all, void* workspace,

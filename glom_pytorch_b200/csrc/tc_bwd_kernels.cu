@@ -27,7 +27,7 @@ constexpr int THREADS = 32 * (EPI_WARPS + 4);
 constexpr uint32_t PATCH_BYTES = 4096;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * PATCH_BYTES + BN * 4 + 256;
 
-enum { BW_PRE = 0, BW_DH = 1, BW_DX = 2, BW_DW = 3 };
+enum { BW_PRE = 0, BW_DH = 1, BW_DX = 2, BW_DW = 3, BW_BATCH = 4 };
 
 struct BwdParams {
   int rows, d, L, n, G;
@@ -41,6 +41,13 @@ struct BwdParams {
   float* dx;           // (R, G, d) fp32
   // weight gradients in the reference layout (accumulated into)
   float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
+  // BW_BATCH: C[z] (M = n rows, N cols) (+)= A[z] . B[z]^T-like, z = (image, level); operands come from 3-D tensor
+  // maps over state-like (R, L*d) tensors (inner offset l*d, batch = image) or attention-like (Z, n, n) ones
+  int bN, bK;                // N and K extents
+  int a_mn, b_mn;            // 1: operand is MN-major (k runs over rows of the source), 0: K-major
+  int a_state, b_state;      // 1: state-like source, 0: attention-like
+  int out_kind;              // 0: store (Z, n, n) fp32; 1: accumulate into state-like fp32; 2: store state-like fp32
+  float* out;
 };
 
 struct Tile {
@@ -57,6 +64,10 @@ __device__ __forceinline__ Tile decode(const BwdParams& p, int tile) {
   } else if (MODE == BW_DX) {                        // output (R, d) per group
     const int nn = p.d / BN, nm = (p.rows + 255) / 256;
     t.n_blk = tile % nn; t.m_blk = (tile / nn) % nm; t.g = tile / (nn * nm); t.num_kb = 4 * p.d / BK;
+  } else if (MODE == BW_BATCH) {
+    const int nm = (p.n + 255) / 256, nn = (p.bN + BN - 1) / BN;
+    t.n_blk = tile % nn; t.m_blk = (tile / nn) % nm; t.g = tile / (nn * nm);      // g = problem z
+    t.num_kb = (p.bK + BK - 1) / BK;
   } else {                                           // weight gradients: 2 * (d/256) * (4d/256) tiles per group
     const int per_kind = (p.d / 256) * (4 * p.d / BN);
     t.g = tile / (2 * per_kind);
@@ -152,6 +163,15 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
             const int m128 = t.m_blk * 2 + (int)cta_rank;
             tma_load_2d_2sm(sa, &map_a0, bar, 0, ((t.g * p.m128 + m128) * kbg_n + kb) * BM);    // dpre block (16 KB)
             tma_load_2d_2sm(sb, &map_b, bar, kb * BK, t.g * p.d + t.n_blk * BN + (int)cta_rank * (BN / 2));
+          } else if (MODE == BW_BATCH) {
+            const int z = t.g, bb = z / p.L, lv = z % p.L;
+            const int a_off = p.a_state ? lv * p.d : 0, a_bt = p.a_state ? bb : z;
+            const int b_off = p.b_state ? lv * p.d : 0, b_bt = p.b_state ? bb : z;
+            const int mrow = t.m_blk * 256 + (int)cta_rank * BM, ncol = t.n_blk * BN + (int)cta_rank * (BN / 2);
+            if (!p.a_mn) tma_load_3d_2sm(sa, &map_a0, bar, a_off + kb * BK, mrow, a_bt);
+            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sa + i * 8192, &map_a0, bar, a_off + mrow + i * 64, kb * BK, a_bt);
+            if (!p.b_mn) tma_load_3d_2sm(sb, &map_b, bar, b_off + kb * BK, ncol, b_bt);
+            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sb + i * 8192, &map_b, bar, b_off + ncol + i * 64, kb * BK, b_bt);
           } else {
             // TN: k runs over rows.  A tile = 64 k-rows x this CTA's 128 M-columns, B tile = 64 k-rows x this CTA's
             // 128 N-columns, each as two [64 x 64] boxes (MN-major operand: 128-byte rows of 64 consecutive columns).
@@ -178,7 +198,9 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
     }
   } else if (warp == W_MMA) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, MODE == BW_DW ? 1 : 0, MODE == BW_DW ? 1 : 0);
+      const int a_mn = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.a_mn : 0);
+      const int b_mn = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.b_mn : 0);
+      const uint32_t idesc = umma_idesc_bf16(256, BN, a_mn, b_mn);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
@@ -193,14 +215,9 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            uint64_t ad, bd;
-            if (MODE == BW_DW) {   // MN-major: 16 k-rows = 2048 B; the two 64-column blocks are 8192 B apart
-              ad = umma_desc_sw128(a_addr + k * 2048, 8192, 1024);
-              bd = umma_desc_sw128(b_addr + k * 2048, 8192, 1024);
-            } else {
-              ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-              bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            }
+            // MN-major: 16 k-rows = 2048 B, the two 64-column blocks are 8192 B apart; K-major: 32 B per 16 k
+            const uint64_t ad = a_mn ? umma_desc_sw128(a_addr + k * 2048, 8192, 1024) : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = b_mn ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024) : umma_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage], 3);
@@ -270,6 +287,23 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
             }
           } else if (MODE == BW_DX) {
             if (row < p.rows) *reinterpret_cast<float4*>(p.dx + ((size_t)row * p.G + t.g) * p.d + col) = acc;
+          } else if (MODE == BW_BATCH) {
+            const int z = t.g;
+            if (row < p.n && col < p.bN) {
+              if (p.out_kind == 0) {
+                float* dst = p.out + ((size_t)z * p.n + row) * p.bN + col;
+                if ((p.bN & 3) == 0) *reinterpret_cast<float4*>(dst) = acc;
+                else {
+                  const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+                  for (int e = 0; e < 4 && col + e < p.bN; ++e) dst[e] = a4[e];
+                }
+              } else {
+                float* dst = p.out + (((size_t)(z / p.L) * p.n + row) * p.L + (z % p.L)) * p.d + col;
+                float4 o = acc;
+                if (p.out_kind == 1) { const float4 old = *reinterpret_cast<const float4*>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *reinterpret_cast<float4*>(dst) = o;
+              }
+            }
           } else {
             // weight gradient tile: output row = M index (o or j), accumulate into the reference-layout tensor
             const int lw = t.g >> 1;
@@ -333,7 +367,44 @@ cudaError_t launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorM
   return cudaLaunchKernelEx(&cfg, bwd_gemm_kernel<MODE>, a0, a1, a2, b0, b1, b2, p);
 }
 
+bool map3d_box(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
+               uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, char* err, size_t errlen,
+               const char* what) {
+  cuuint64_t gd[3] = {inner, rows, batches};
+  cuuint64_t gs[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+  cuuint32_t bx[3] = {(cuuint32_t)BK, box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gd, gs, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return false; }
+  return true;
+}
+
 }  // namespace
+
+// Batched C[z] (n x N) (+)= A[z] B[z] on tensor cores for the attention backward (z = image * L + level).
+//   state-like operands: bf16 (B*n, L*d) tensors; attention-like: bf16 (Z, n, n).  a_mn / b_mn: see BwdParams.
+int attn_bwd_gemm_tc(const Geometry& g, const void* a_src, int a_state, int a_mn, const void* b_src, int b_state, int b_mn,
+                     int N, int K, int out_kind, float* out, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
+                     char* err, size_t errlen) {
+  const int n = g.n, L = g.L, d = g.d, Z = g.B * L;
+  CUtensorMap ma, mb;
+  auto mk = [&](CUtensorMap* m, const void* src, int state, int mn, const char* what) {
+    const uint32_t box_rows = mn ? 64u : (uint32_t)BM;
+    if (state) return map3d_box(enc, m, src, (uint64_t)L * d, n, g.B, (uint64_t)L * d, (uint64_t)n * L * d, box_rows, err, errlen, what);
+    return map3d_box(enc, m, src, n, n, Z, n, (uint64_t)n * n, box_rows, err, errlen, what);
+  };
+  if (!mk(&ma, a_src, a_state, a_mn, "attn-bwd A") || !mk(&mb, b_src, b_state, b_mn, "attn-bwd B")) return -3;
+  BwdParams p{};
+  p.rows = g.rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+  p.bN = N; p.bK = K; p.a_mn = a_mn; p.b_mn = b_mn; p.a_state = a_state; p.b_state = b_state; p.out_kind = out_kind; p.out = out;
+  p.num_tiles = Z * ((n + 255) / 256) * ((N + BN - 1) / BN);
+  cudaError_t e = launch<BW_BATCH>(ma, ma, ma, mb, mb, mb, p, num_sms, st);
+  if (launches) ++*launches;
+  if (e != cudaSuccess) { snprintf(err, errlen, "attention-backward gemm launch: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
 
 // One reverse step of the MLPs on tensor cores.  Inputs are bf16 shadows prepared by the caller:
 //   xb (R, d), sb (R, L*d), sp (R, (L-1)*d) of S_t ; gsb (R, L*d) = bf16(dL/dS_{t+1} / c)
