@@ -99,11 +99,15 @@ static cudaError_t gemm_f32(const GemmF32& q, int batches, cudaStream_t st, int*
 // g (R, L, d)  <-  gin (R, L, d) / c_l        (:142);   ds (R, L, d) <- g (residual term of the sum, :141)
 __global__ void scale_by_contrib_kernel(size_t total, int L, int d, const float* __restrict__ gin,
                                         float* __restrict__ g, float* __restrict__ ds) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int l = (int)((i / d) % L);
-    const float v = gin[i] / ((l == L - 1) ? 3.0f : 4.0f);
-    g[i] = v;
-    ds[i] = v;
+  const size_t total4 = total / 4;
+  const unsigned d4 = (unsigned)d / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned l = (unsigned)((i / d4) % (unsigned)L);
+    float4 v = reinterpret_cast<const float4*>(gin)[i];
+    if (l == (unsigned)L - 1) { v.x /= 3.0f; v.y /= 3.0f; v.z /= 3.0f; v.w /= 3.0f; }
+    else { v.x *= 0.25f; v.y *= 0.25f; v.z *= 0.25f; v.w *= 0.25f; }
+    reinterpret_cast<float4*>(g)[i] = v;
+    reinterpret_cast<float4*>(ds)[i] = v;
   }
 }
 // xp (R, d) = S[:, l, :] + pos[row % n]     (top-down input, :136)
@@ -127,22 +131,23 @@ __global__ void gelu_bwd_kernel(size_t total, const float* __restrict__ pre, flo
     dh[i] = dh[i] * (cdf + x * pdf);
   }
 }
-// out[c] += sum_r src[r * row_stride + c]          (bias gradients)
+// out[c] += sum_r src[r * row_stride + c]          (bias gradients); grid (cols / 32, row chunks)
 __global__ void colsum_acc_kernel(int rows, int cols, long long row_stride, const float* __restrict__ src,
                                   float* __restrict__ out) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5;                 // 8 row slices per block
+  const int r_begin = (int)(((long long)rows * blockIdx.y) / gridDim.y), r_end = (int)(((long long)rows * (blockIdx.y + 1)) / gridDim.y);
   __shared__ float red[8][33];
   float acc = 0.f;
   if (c < cols)
-    for (int r = part; r < rows; r += 8) acc += src[(long long)r * row_stride + c];
+    for (int r = r_begin + part; r < r_end; r += 8) acc += src[(long long)r * row_stride + c];
   red[part][threadIdx.x & 31] = acc;
   __syncthreads();
   if (part == 0 && c < cols) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
-    out[c] += s;
+    atomicAdd(out + c, s);
   }
 }
 // dpos[nn, c] += sum_b dx[(b * n + nn), c]          (positional-embedding gradient, :136)
@@ -252,13 +257,14 @@ __global__ void normalize_bwd_kernel(int nrows, int d, const float* __restrict__
   const float r = rnorm[row];
   for (int c = lane; c < d; c += 32) ds[(size_t)row * d + c] += (g[c] - k[c] * dot) * r;
 }
-// dinit[l, c] = sum over rows of g[(row, l, c)]           (broadcast of init_levels, :124)
+// dinit[l, c] = sum over rows of g[(row, l, c)]           (broadcast of init_levels, :124); grid (L*d/256, row chunks)
 __global__ void init_grad_kernel(int rows, int L, int d, const float* __restrict__ g, float* __restrict__ dinit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * d) return;
+  const int r_begin = (int)(((long long)rows * blockIdx.y) / gridDim.y), r_end = (int)(((long long)rows * (blockIdx.y + 1)) / gridDim.y);
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += g[(size_t)r * L * d + i];
-  dinit[i] += acc;
+  for (int r = r_begin; r < r_end; ++r) acc += g[(size_t)r * L * d + i];
+  atomicAdd(dinit + i, acc);
 }
 
 __global__ void cast_bf16_rows(size_t n4, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
@@ -361,12 +367,12 @@ static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const
       // dW2 += DY^T h                                     (d x 4d)
       q = GemmF32{d, h4, R, 1, Mat{DY.p, 1, ld, 0, 0}, Mat{hb, h4, 1, 0, 0}, MatOut{dw2 + (size_t)l * d * h4, h4, 1, 0, 0}, 1.f, 1.f, nullptr};
       CK(gemm_f32(q, 1, st, launches));
-      colsum_acc_kernel<<<(d + 31) / 32, 256, 0, st>>>(R, d, ld, DY.p, db2 + (size_t)l * d);
+      colsum_acc_kernel<<<dim3((d + 31) / 32, 16), 256, 0, st>>>(R, d, ld, DY.p, db2 + (size_t)l * d);
       CKL();
       // dW1 += dpre^T X                                   (4d x d)
       q = GemmF32{h4, d, R, 1, Mat{dh, 1, h4, 0, 0}, Mat{X.p, X.s_row, 1, 0, 0}, MatOut{dw1 + (size_t)l * h4 * d, d, 1, 0, 0}, 1.f, 1.f, nullptr};
       CK(gemm_f32(q, 1, st, launches));
-      colsum_acc_kernel<<<(h4 + 31) / 32, 256, 0, st>>>(R, h4, h4, dh, db1 + (size_t)l * h4);
+      colsum_acc_kernel<<<dim3((h4 + 31) / 32, 16), 256, 0, st>>>(R, h4, h4, dh, db1 + (size_t)l * h4);
       CKL();
       // dX = dpre W1                                      (R x d)
       q = GemmF32{R, d, h4, 1, Mat{dh, h4, 1, 0, 0}, Mat{W1, d, 1, 0, 0}, MatOut{dx, d, 1, 0, 0}, 1.f, 0.f, nullptr};
@@ -503,23 +509,34 @@ __global__ void pos_grad_all_kernel(int B, int n, int L, int d, const float* __r
   }
 }
 // first-layer bias gradients: column sums of the blocked bf16 dpre (G, m128, 4d/64, 128, 64)
+// grid (4d/64, G, row chunks); thread = (8-column group, row lane): 16-byte loads along the 128-byte block rows
 __global__ void colsum_blocked_kernel(int rows, int m128, int d, int L, const __nv_bfloat16* __restrict__ dpre,
                                       float* __restrict__ d_bu_b1, float* __restrict__ d_td_b1) {
   const int h = 4 * d, kbg = h / 64;
-  const int g = blockIdx.y, cb = blockIdx.x;            // group, 64-column block
-  const int col = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 row slices
-  __shared__ float red[4][64];
-  float acc = 0.f;
-  for (int r = part; r < rows; r += 4) {
-    const size_t off = ((size_t)((g * m128 + (r >> 7)) * kbg + cb) * 128 + (r & 127)) * 64 + col;
-    acc += __bfloat162float(dpre[off]);
+  const int g = blockIdx.y, cb = blockIdx.x;
+  const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;        // 8 column groups x 32 row lanes
+  const int r_begin = (int)(((long long)rows * blockIdx.z) / gridDim.z), r_end = (int)(((long long)rows * (blockIdx.z + 1)) / gridDim.z);
+  float acc[8] = {};
+  for (int r = r_begin + rl; r < r_end; r += 32) {
+    const size_t off = ((size_t)((g * m128 + (r >> 7)) * kbg + cb) * 128 + (r & 127)) * 64 + c8 * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(dpre + off);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] += __uint_as_float(w[i] << 16);
+      acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+    }
   }
-  red[part][col] = acc;
+  __shared__ float red[32][65];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][c8 * 8 + i] = acc[i];
   __syncthreads();
-  if (part == 0) {
-    const float s = red[0][col] + red[1][col] + red[2][col] + red[3][col];
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
     float* dst = (g & 1) ? d_td_b1 : d_bu_b1;
-    dst[(size_t)(g >> 1) * h + cb * 64 + col] += s;
+    atomicAdd(dst + (size_t)(g >> 1) * h + cb * 64 + threadIdx.x, s);
   }
 }
 
@@ -607,11 +624,11 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
       CKLI();
       pos_grad_all_kernel<<<nblk((size_t)g.n * g.d), 256, 0, st>>>(g.B, g.n, g.L, g.d, m.dx, a.d_pos);
       CKLI();
-      colsum_acc_kernel<<<(g.L * g.d + 31) / 32, 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2);
+      colsum_acc_kernel<<<dim3((g.L * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2);
       CKLI();
-      colsum_acc_kernel<<<((g.L - 1) * g.d + 31) / 32, 256, 0, st>>>(g.rows, (g.L - 1) * g.d, (long long)g.L * g.d, gs, a.d_td_b2);
+      colsum_acc_kernel<<<dim3(((g.L - 1) * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, (g.L - 1) * g.d, (long long)g.L * g.d, gs, a.d_td_b2);
       CKLI();
-      colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
+      colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G, 8), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
       CKLI();
     }
     CKI(cudaMemcpyAsync(G, ds, state * 4, cudaMemcpyDeviceToDevice, st));
@@ -625,7 +642,7 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
     CKLI();
   }
   if (a.d_init) {
-    init_grad_kernel<<<(g.L * g.d + 255) / 256, 256, 0, st>>>(g.rows, g.L, g.d, G, a.d_init);
+    init_grad_kernel<<<dim3((g.L * g.d + 255) / 256, 64), 256, 0, st>>>(g.rows, g.L, g.d, G, a.d_init);
     CKLI();
   }
   return 0;

@@ -1,8 +1,8 @@
 // Tensor-core backward of the two grouped MLPs (SURVEY 8 row f2, bf16 engine).
 //
 // Per reverse step and MLP group g (bottom-up l / top-down l), with x the group's input rows, dY = dL/dS_{t+1}[:, l]/c_l:
-//   P  : pre  = x W1^T + b1                      (NT GEMM, K = d)        -> bf16, 16 KB blocks like the forward's H
-//   H  : dh   = dY W2 ;  h = gelu(pre), dpre = dh * gelu'(pre)           (NT GEMM, K = d, B = W2^T)   -> h, dpre blocks
+//   P  : pre  = x W1^T + b1 ;  h = gelu(pre), gp = gelu'(pre)  (NT GEMM, K = d) -> bf16, 16 KB blocks like the forward's H
+//   H  : dh   = dY W2 ;  dpre = dh * gp                        (NT GEMM, K = d, B = W2^T)   -> dpre blocks
 //   X  : dx   = dpre W1                          (NT GEMM, K = 4d, B = W1^T)  -> fp32 (R, G, d)
 //   W  : dW2 += dY^T h ;  dW1 += dpre^T x        (TN GEMMs, K = rows; both operands read MN-major by TMA)
 // All four run on CTA pairs (cta_group::2, UMMA 256 x 256 x 16) with the forward's pipeline structure: warp-specialised
@@ -265,24 +265,24 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
               // blocked address: block (g, row / 128, col / 64), row % 128, col % 64
               const size_t off = ((size_t)((t.g * p.m128 + (row >> 7)) * kbg_n + (col >> 6)) * BM + (row & 127)) * BK + (col & 63);
               if (MODE == BW_PRE) {
+                // pre-activation -> h = gelu(pre) and gp = gelu'(pre), both bf16 (the `pre` buffer holds gp)
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + part * PART_COLS + c0 + c * 4);
-                *reinterpret_cast<uint2*>(p.pre + off) =
-                    make_uint2(pack_bf16x2(acc.x + b4.x, acc.y + b4.y), pack_bf16x2(acc.z + b4.z, acc.w + b4.w));
-              } else {
-                const uint2 pw = *reinterpret_cast<const uint2*>(p.pre + off);
-                const float x[4] = {__uint_as_float(pw.x << 16), __uint_as_float(pw.x & 0xFFFF0000u),
-                                    __uint_as_float(pw.y << 16), __uint_as_float(pw.y & 0xFFFF0000u)};
-                const float dh[4] = {acc.x, acc.y, acc.z, acc.w};
-                float hv[4], dp[4];
+                const float x[4] = {acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w};
+                float hv[4], gp[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float cdf, pdf;
                   normal_cdf_pdf(x[e], cdf, pdf);
                   hv[e] = x[e] * cdf;
-                  dp[e] = dh[e] * fmaf(x[e], pdf, cdf);
+                  gp[e] = fmaf(x[e], pdf, cdf);
                 }
                 *reinterpret_cast<uint2*>(p.h + off) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
-                *reinterpret_cast<uint2*>(p.dpre + off) = make_uint2(pack_bf16x2(dp[0], dp[1]), pack_bf16x2(dp[2], dp[3]));
+                *reinterpret_cast<uint2*>(p.pre + off) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
+              } else {
+                const uint2 pw = *reinterpret_cast<const uint2*>(p.pre + off);       // gelu'(pre)
+                *reinterpret_cast<uint2*>(p.dpre + off) =
+                    make_uint2(pack_bf16x2(acc.x * __uint_as_float(pw.x << 16), acc.y * __uint_as_float(pw.x & 0xFFFF0000u)),
+                               pack_bf16x2(acc.z * __uint_as_float(pw.y << 16), acc.w * __uint_as_float(pw.y & 0xFFFF0000u)));
               }
             }
           } else if (MODE == BW_DX) {
