@@ -228,6 +228,9 @@ def main():
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train", action="store_true",
+                    help="also time a training step (forward with return_all + backward of a loss on all_levels[7,:,:,-1], "
+                         "README.md:58-90) and add it to the JSON line as \"train\"")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -349,6 +352,31 @@ def main():
         barrier()
         ms_e2e = ee0.elapsed_time(ee1)
 
+    train = None
+    if args.train:
+        model.train()
+        tt = 7 if T >= 7 else T
+        for _ in range(2):
+            model.zero_grad(set_to_none=True)
+            model(dev_imgs[0], iters=T, return_all=True)[tt, :, :, -1].square().mean().backward()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        nrep = max(3, args.steps // 4)
+        f_ms = b_ms = 0.0
+        for i in range(nrep):
+            model.zero_grad(set_to_none=True)
+            ev[0].record(stream)
+            loss = model(dev_imgs[i % NBUF], iters=T, return_all=True)[tt, :, :, -1].square().mean()
+            ev[1].record(stream)
+            loss.backward()
+            ev[2].record(stream)
+            torch.cuda.synchronize(dev)
+            f_ms += ev[0].elapsed_time(ev[1]); b_ms += ev[1].elapsed_time(ev[2])
+        train = {"forward_ms": f_ms / nrep, "backward_ms": b_ms / nrep, "reps": nrep,
+                 "value": B * N_PATCH * L * T / ((f_ms + b_ms) / nrep * 1e-3), "unit": "column-iterations/s per GPU (fwd+bwd)",
+                 "loss": f"mean(all_levels[{tt}, :, :, -1] ** 2)", "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        model.eval()
+
     if distributed:
         t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,6 +438,8 @@ def main():
             "clocks": clocks,
             "roofline": roof,
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             v, sec, cores = cpu_port_run(4, 3, 3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),

@@ -143,7 +143,7 @@ class _ColumnUpdate(torch.autograd.Function):
         with torch.cuda.device(device):
             cfg = module.engine_cfg(n)           # bf16 engine: MLP GEMMs of the backward on tensor cores
             ws_bytes = _native.backward_workspace_bytes(cfg, b)
-            ws = _aligned_bytes(ws_bytes, device)
+            ws = module._get_workspace(ws_bytes, device, "_bwd_workspace")      # cached across steps
             _native.backward(cfg, [w.data_ptr() for w in wts], tokens.data_ptr(), pos.data_ptr(), states.data_ptr(),
                              grad_out.data_ptr(), {k: (None if v is None else v.data_ptr()) for k, v in g.items()},
                              b, iters, ctx.return_all, ws.data_ptr(), ws.numel(),
@@ -205,10 +205,11 @@ class Glom(nn.Module):
         self._packed = (key, packed)
         return packed
 
-    def _get_workspace(self, nbytes, device):
-        ws = self._workspace
+    def _get_workspace(self, nbytes, device, slot="_workspace"):
+        ws = getattr(self, slot, None)
         if ws is None or ws.device != device or ws.numel() < nbytes:
-            self._workspace = ws = _aligned_bytes(nbytes, device)
+            ws = _aligned_bytes(nbytes, device)
+            setattr(self, slot, ws)
         return ws
 
     def engine_cfg(self, n, precision=None):
