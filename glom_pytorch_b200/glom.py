@@ -227,15 +227,14 @@ class Glom(nn.Module):
         if not self.use_native_tokenizer:
             return lin(self.image_to_tokens[0](img.float())).contiguous()
         img = img.float().contiguous()
-        out = torch.empty(b, (h // p) * (w // p), self.dim, dtype=torch.float32, device=img.device)
-        wt, bs = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
-        tws_bytes = _native.tokenize_workspace_bytes(b, h, w, p, self.dim, self.precision)
-        tws = getattr(self, "_tok_ws", None)
-        if tws_bytes and (tws is None or tws.device != img.device or tws.numel() < tws_bytes):
-            self._tok_ws = tws = _aligned_bytes(tws_bytes, img.device)
-        _native.tokenize(img.data_ptr(), wt.data_ptr(), bs.data_ptr(), out.data_ptr(), b, h, w, p, self.dim,
-                         self.precision, tws.data_ptr() if tws_bytes else None, tws_bytes,
-                         torch.cuda.current_stream(img.device).cuda_stream)
+        with torch.cuda.device(img.device):      # the library launches on the CURRENT device
+            out = torch.empty(b, (h // p) * (w // p), self.dim, dtype=torch.float32, device=img.device)
+            wt, bs = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+            tws_bytes = _native.tokenize_workspace_bytes(b, h, w, p, self.dim, self.precision)
+            tws = self._get_workspace(tws_bytes, img.device, "_tok_ws") if tws_bytes else None
+            _native.tokenize(img.data_ptr(), wt.data_ptr(), bs.data_ptr(), out.data_ptr(), b, h, w, p, self.dim,
+                             self.precision, tws.data_ptr() if tws_bytes else None, tws_bytes,
+                             torch.cuda.current_stream(img.device).cuda_stream)
         self._tok_launches = _native.last_launch_count()
         return out
 
