@@ -56,6 +56,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// same with acquire semantics at cluster scope: the arrivals come from the peer CTA (mbar_arrive_cluster after a
+// fence.proxy.async; a release.cluster arrive costs a GPU-scope MEMBAR per warp and item and is not needed for
+// shared-memory data consumed by the tensor core of the writing CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  auto try_wait = [&]() -> uint32_t {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+  };
+  if (try_wait()) return;
+  const long long t0 = clock64();
+  while (!try_wait()) {
+    if (clock64() - t0 > GLOM_WAIT_TIMEOUT_CYCLES) {
+      printf("glom_b200: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (TMA/UMMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -480,24 +480,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
 }
 
 // =====================================================================================
-// K3: consensus attention.  CTA = (query tile of 128, level l, image b).
-//   phase 1: S = Q K^T per key block (<= 256 keys) over d, fp32 in TMEM; softmax warps turn each
-//            block into unnormalised bf16 probabilities P in shared memory (UMMA A-operand layout)
-//   phase 2: O = P V per 256-wide slice of d (V read MN-major straight from the state shadow),
-//            scaled by 1/rowsum and written as bf16 C.
+// K3: consensus attention on CTA pairs.  Persistent clusters of two CTAs (one per SM); a work item is
+// (pair of 128-query tiles, level l, image b), CTA r of the pair owning query tile 2u + r.
+//   phase 1: S = Q K^T per key block (<= 256 keys) over d as one 256 x w cta_group::2 MMA: each CTA feeds its
+//            own 128 query rows and HALF of the key block and receives its rows of S (fp32) in a 256-column TMEM
+//            buffer.  The softmax warps turn them into unnormalised bf16 probabilities P in shared memory
+//            (UMMA A-operand layout).
+//   phase 2: O = P V in 256-wide slices of d (V read MN-major straight from the state shadow, each CTA
+//            feeding half of the slice's columns); each slice is scaled by 1/rowsum and written as bf16 C while
+//            the next one is being multiplied.
+// Every byte of the state shadow is therefore fetched once per pair and phase instead of once per query tile,
+// which halves the L2 -> shared-memory traffic.  The TMA / MMA threads keep their ring and buffer counters
+// running across items: the two TMEM buffers alternate S, O0, O1, S', O0', ... so Q K^T of item i+1 is issued
+// as soon as slice 0 of item i has been read out and overlaps the rest of its output phase.
+// Softmax stabiliser: every key is unit-normalised, so |logit_ij| <= |S_i| d^-1/2 (Cauchy-Schwarz); that bound
+// replaces the row maximum (softmax is shift-invariant) and S is read from TMEM once instead of twice.  The
+// diagonal is never masked (its logit is -5e-4 or, with attend_self, ~ the bound itself), so the row sum cannot
+// underflow while the bound stays below 2^BOUND_MAX; rows beyond that take the exact-maximum pass.
+// With n in (240, 256] a CTA's query tile IS its half of the single key block and is not loaded separately.
+// Measured (profiles/README.md): the softmax / output warps are bound by TMEM read-out (64 B/clk/SM), the XU pipe
+// (ex2 + fp32->bf16 packing) and the burst of C stores, the Q K^T phase by the first touch of the shadow in HBM.
 // =====================================================================================
-constexpr int ATTN_SM_WARPS = 8;                  // softmax / output warps: 4 TMEM quadrants x 2 column halves
-constexpr int ATTN_THREADS = 384;                 // 8 softmax warps + TMA + MMA + TMEM-alloc + 1 idle
+constexpr int ATTN_SM_WARPS = 16;                 // softmax / output warps: 4 TMEM quadrants x 4 column parts
+constexpr int ATTN_THREADS = 640;                 // 16 softmax warps + TMA + MMA + TMEM-alloc + 1 idle
+constexpr int ATTN_RED_FLOATS = 1536;             // block maxima [2][4][128] + row sums [4][128]
 constexpr int ATTN_SM_THREADS = ATTN_SM_WARPS * 32;
 constexpr int ATTN_MAX_KB = 4;
-constexpr uint32_t ATTN_STAGE_BYTES = A_STAGE_BYTES + 256 * 128;   // Q tile + K block (or V slice)
+constexpr uint32_t ATTN_SLOT_BYTES = 32768;       // ring slot: Q + K-half chunk(s), or 2 key chunks x 2 column boxes of V
+constexpr uint32_t ATTN_PATCH_BYTES = ATTN_SM_WARPS * 2048;
+constexpr float ATTN_BOUND_MAX = 96.f;            // log2 units
 
 struct AttnParams {
   int n, L, d;
   int attend_self, mask_side, mask_d2_max;
   int n_pad16, n_pad64, nkb, nchunk;   // key padding, key blocks (<=256), 64-key chunks
-  int kbox_rows;                       // rows fetched per K box
+  int khalf_rows;                      // rows fetched per K box: half of the (widest) key block
   int num_stages;
+  int q_in_k;                          // 1: the CTA's query tile is its half of the single key block
+  int npairs, num_items;               // query-tile pairs per (l, b); npairs * L * B
   int nparts;
   const float* nsq;                    // (rows, L, nparts) squared-norm partials of the state
   __nv_bfloat16* c_out;                // (rows, L, d)
@@ -506,7 +526,7 @@ struct AttnParams {
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64, 128, 1)
-            const __grid_constant__ CUtensorMap map_k,    // box (64, kbox_rows, 1)
+            const __grid_constant__ CUtensorMap map_k,    // box (64, khalf_rows, 1)
             const __grid_constant__ CUtensorMap map_v,    // box (64, 64, 1)
             const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -515,279 +535,405 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* p_smem = smem;                                                  // nchunk x [128 x 64] bf16, SW128
   uint8_t* stages = p_smem + (size_t)p.nchunk * A_STAGE_BYTES;
-  float* rs = reinterpret_cast<float*>(stages + (size_t)p.num_stages * ATTN_STAGE_BYTES);   // [n_pad16]
-  float* red = rs + p.n_pad16;                                              // [768]: block max x2 parities, row sums
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 768);
-  uint64_t* empty_bar = full_bar + p.num_stages;
-  uint64_t* afull_bar = empty_bar + p.num_stages;
-  uint64_t* aempty_bar = afull_bar + 2;
-  uint64_t* pready_bar = aempty_bar + 2;
+  uint8_t* patches = stages + (size_t)p.num_stages * ATTN_SLOT_BYTES;      // 16 x 2 KB transpose patches
+  float* rs = reinterpret_cast<float*>(patches + ATTN_PATCH_BYTES);        // [2][n_pad16] per-key scales, by item parity
+  float* bnd = rs + 2 * p.n_pad16;                                         // [2][n_pad16] per-row logit bounds
+  uint32_t* key_hw = reinterpret_cast<uint32_t*>(bnd + 2 * p.n_pad16);     // [n_pad16] (grid row << 16) | grid column
+  float* red = reinterpret_cast<float*>(key_hw + p.n_pad16);               // block maxima (2 parities), row sums
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + ATTN_RED_FLOATS); // leader's: both CTAs' TMA bytes
+  uint64_t* empty_bar = full_bar + p.num_stages;                           // own: slot consumed by the pair MMA
+  uint64_t* afull_bar = empty_bar + p.num_stages;      // own [2]: S block / O slice complete in TMEM buffer
+  uint64_t* aempty_bar = afull_bar + 2;                // leader's [2]: buffer drained by the softmax warps of both CTAs
+  uint64_t* pready_bar = aempty_bar + 2;               // leader's: P of the item complete in both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pready_bar + 1);
 
-  // softmax / output warps are warps 0-7, control warps 8-10 (higher ids win the warp arbiter)
+  // softmax / output warps are warps 0-15, control warps 16-18 (higher ids win the warp arbiter)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int W_TMA = ATTN_SM_WARPS, W_MMA = ATTN_SM_WARPS + 1, W_ALLOC = ATTN_SM_WARPS + 2;
-  const int q0 = blockIdx.x * BM, l = blockIdx.y, b = blockIdx.z;
-  const int npass = (p.d + 255) / 256;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int nsub = (p.d + 255) / 256;                  // O slices per item
+  const int nvslot = (p.nchunk + 1) / 2;               // ring slots per O slice (two 64-key chunks each)
+  const int cps = p.q_in_k ? 2 : 1;                    // d-chunks of Q K^T per ring slot
+  const uint32_t kv_off = p.q_in_k ? 0u : A_STAGE_BYTES;
+  const int pairs_per_img = p.npairs * p.L;
 
   if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], ATTN_SM_THREADS); }
-    mbar_init(pready_bar, ATTN_SM_THREADS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 2 * ATTN_SM_WARPS); }
+    mbar_init(pready_bar, 2 * ATTN_SM_WARPS);
     fence_barrier_init();
   }
-  if (warp == W_ALLOC) tmem_alloc(tmem_slot, 512);
+  if (warp == W_ALLOC) tmem_alloc_2sm(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();          // peer barriers initialised + both TMEM allocations done before any cross-CTA traffic
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
 
   if (warp == W_TMA) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        for (int dc = 0; dc < p.d / BK; ++dc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* s = stages + (size_t)stage * ATTN_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (uint32_t)p.kbox_rows * 128u);
-          tma_load_3d(s, &map_q, &full_bar[stage], l * p.d + dc * BK, q0, b);
-          tma_load_3d(s + A_STAGE_BYTES, &map_k, &full_bar[stage], l * p.d + dc * BK, kb * 256, b);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      for (int it = cluster_id; it < p.num_items; it += num_clusters) {
+        const int b = it / pairs_per_img, l = (it % pairs_per_img) / p.npairs;
+        const int q0 = (2 * (it % p.npairs) + (int)cta_rank) * BM;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int w = min(256, p.n_pad16 - kb * 256);
+          const int key0 = kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
+          for (int dc = 0; dc < p.d / BK; dc += cps) {
+            const int nc = min(cps, p.d / BK - dc);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* s = stages + (size_t)stage * ATTN_SLOT_BYTES;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)nc * (kv_off + (uint32_t)p.khalf_rows * 128u));
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            for (int c = 0; c < nc; ++c) {
+              if (!p.q_in_k) tma_load_3d_2sm(s, &map_q, bar, l * p.d + (dc + c) * BK, q0, b);
+              tma_load_3d_2sm(s + kv_off + c * 16384, &map_k, bar, l * p.d + (dc + c) * BK, key0, b);
+            }
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
         }
-      }
-      for (int ps = 0; ps < npass; ++ps) {
-        const int wd = min(256, p.d - ps * 256);
-        for (int kc = 0; kc < p.nchunk; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* s = stages + (size_t)stage * ATTN_STAGE_BYTES + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(wd / 64) * 8192u);
-          for (int i = 0; i < wd / 64; ++i)
-            tma_load_3d(s + i * 8192, &map_v, &full_bar[stage], l * p.d + ps * 256 + i * 64, kc * 64, b);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        for (int sp = 0; sp < nsub; ++sp) {
+          const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;     // slice width as issued (128 or 256)
+          const int nbox = wdp >> 7;                                   // 64-column boxes in this CTA's half
+          for (int vs = 0; vs < nvslot; ++vs) {
+            const int nkc = min(2, p.nchunk - 2 * vs);               // 64-key chunks in this slot
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* s = stages + (size_t)stage * ATTN_SLOT_BYTES;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(nkc * nbox) * 8192u);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            for (int kc = 0; kc < nkc; ++kc)
+              for (int i = 0; i < nbox; ++i) {
+                const int dcol = sp * 256 + (int)cta_rank * (wdp >> 1) + i * 64;   // this CTA's half of the slice
+                tma_load_3d_2sm(s + kc * 16384 + i * 8192, &map_v, bar, dcol < p.d ? l * p.d + dcol : p.L * p.d,
+                                (2 * vs + kc) * 64, b);                            // past d: out of bounds -> zeros
+              }
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
       int stage = 0; uint32_t phase = 0;
-      int job = 0;
-      // phase 1: S_kb = Q K_kb^T
-      for (int kb = 0; kb < p.nkb; ++kb, ++job) {
-        const int w = min(256, p.n_pad16 - kb * 256);
-        const uint32_t idesc = umma_idesc_bf16(BM, w, 0, 0);
-        const int buf = job & 1;
-        mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-        for (int dc = 0; dc < p.d / BK; ++dc) {
-          mbar_wait(&full_bar[stage], phase);
+      uint32_t job = 0, item_par = 0;
+      for (int it = cluster_id; it < p.num_items; it += num_clusters, item_par ^= 1) {
+        // phase 1: S_kb = Q K_kb^T
+        for (int kb = 0; kb < p.nkb; ++kb, ++job) {
+          const int w = min(256, p.n_pad16 - kb * 256);
+          const uint32_t idesc = umma_idesc_bf16(256, w, 0, 0);
+          const uint32_t buf = job & 1;
+          mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(stages + (size_t)stage * ATTN_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint32_t d_tmem = tmem_base + buf * 256u;
+          for (int dc = 0; dc < p.d / BK; dc += cps) {
+            const int nc = min(cps, p.d / BK - dc);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t s_addr = smem_u32(stages + (size_t)stage * ATTN_SLOT_BYTES);
+            for (int c = 0; c < nc; ++c) {
+              const uint32_t b_addr = s_addr + kv_off + (uint32_t)c * 16384u;
+              const uint32_t a_addr = p.q_in_k ? b_addr : s_addr;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
-                      idesc, (dc | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                              umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (dc | c | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 3);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(&afull_bar[buf], 3);
         }
-        umma_commit(&afull_bar[buf]);
-      }
-      // phase 2: O = P V   (A = P from smem, K-major; B = V slice, MN-major)
-      mbar_wait(pready_bar, 0);
-      tc_fence_after_sync();
-      for (int ps = 0; ps < npass; ++ps, ++job) {
-        const int wd = min(256, p.d - ps * 256);
-        const uint32_t idesc = umma_idesc_bf16(BM, wd, 0, 1);
-        const int buf = job & 1;
-        mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
+        // phase 2: O = P V   (A = P from smem, K-major; B = V slice, MN-major, 64 columns from each CTA)
+        mbar_wait_cluster(pready_bar, item_par);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-        for (int kc = 0; kc < p.nchunk; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int sp = 0; sp < nsub; ++sp, ++job) {
+          const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;
+          const uint32_t idesc = umma_idesc_bf16(256, wdp, 0, 1);
+          const uint32_t buf = job & 1;
+          mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(p_smem + (size_t)kc * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(stages + (size_t)stage * ATTN_STAGE_BYTES + A_STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + buf * 256u;
+          for (int vs = 0; vs < nvslot; ++vs) {
+            const int nkc = min(2, p.nchunk - 2 * vs);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t s_addr = smem_u32(stages + (size_t)stage * ATTN_SLOT_BYTES);
+            for (int kc = 0; kc < nkc; ++kc) {
+              const uint32_t a_addr = smem_u32(p_smem + (size_t)(2 * vs + kc) * A_STAGE_BYTES);
+              const uint32_t b_addr = s_addr + (uint32_t)kc * 16384u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                      umma_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (kc | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                              umma_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (vs | kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 3);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(&afull_bar[buf], 3);
         }
-        umma_commit(&afull_bar[buf]);
       }
     }
   } else if (warp < ATTN_SM_WARPS) {
-    // ------------------------------------------------------------------ softmax + output warps (8)
-    // warp = (quad, half): TMEM lane quadrant `quad` (32 query rows, one per thread) x column half `half`
-    // of every key block / output slice; row maxima and sums are combined across the two halves in smem.
-    const int quad = warp & 3, half = warp >> 2;
+    // ------------------------------------------------------------------ softmax + output warps (16 per CTA)
+    // warp = (quad, part): TMEM lane quadrant `quad` (32 query rows, one per thread) x column quarter `part`
+    // of every key block / output slice; row sums (and exact maxima) are combined across the four parts in smem.
+    // These loops are chains of dependent latencies (TMEM load -> math -> shared-memory transpose -> store), so
+    // four warps per scheduler are what hides them.
+    const int quad = warp & 3, part = warp >> 2;
     const int t = quad * 32 + lane;          // query row inside the tile == TMEM lane
-    const int qi = q0 + t;
     const int tid = threadIdx.x;
-    const size_t img_row0 = (size_t)b * p.n;
     constexpr float LOG2E = 1.4426950408889634f;
     const float NEG_INF = __int_as_float(0xff800000);
-
-    // per-key scale  d^-1/2 / max(|S_j|, 1e-12)   (F.normalize eps, :58)
-    for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS) {
-      float v = 0.f;
-      if (j < p.n) {
-        const float* ns = p.nsq + ((img_row0 + j) * p.L + l) * p.nparts;
-        float ss = 0.f;
-        for (int i = 0; i < p.nparts; ++i) ss += ns[i];
-        v = p.scale / fmaxf(sqrtf(ss), 1e-12f);
-      }
-      rs[j] = v;
-    }
-    named_bar_sync(1, ATTN_SM_THREADS);
-
     const bool use_mask = p.mask_side > 0;
-    const int qh = use_mask ? qi / p.mask_side : 0, qw = use_mask ? qi % p.mask_side : 0;
-    const int diag = p.attend_self ? -1 : qi;
-    auto logit = [&](uint32_t raw, int j) -> float {
-      float sv = __uint_as_float(raw) * rs[j];                                      // (:60)
-      sv = (j == diag) ? -5e-4f : sv;                                               // (:62-65)
-      bool masked = j >= p.n;
-      if (use_mask) {                                                               // (:67-69)
-        const int dh = qh - j / p.mask_side, dw = qw - j % p.mask_side;
-        masked |= (dh * dh + dw * dw > p.mask_d2_max);
-      }
-      return masked ? NEG_INF : sv;
-    };
+    uint8_t* patch = patches + (size_t)warp * 2048;
+    // releases towards the leader's MMA issuer: one arrival per warp of either CTA
+    const uint32_t pready_remote = mapa_shared(smem_u32(pready_bar), 0);
+    const uint32_t aempty_remote = mapa_shared(smem_u32(&aempty_bar[0]), 0);     // [buf]: + 8 * buf
 
-    float m_run = NEG_INF, l_run = 0.f;      // l_run: this warp's column half only
-    float m_used[ATTN_MAX_KB];
-    int job = 0;
-    for (int kb = 0; kb < p.nkb; ++kb, ++job) {
-      const int w = min(256, p.n_pad16 - kb * 256);
-      const int wlo = ((w >> 5) + ((w >> 4) & 1)) << 4;      // columns of half 0 (multiple of 16, >= w/2)
-      const int cbeg = half ? wlo : 0, cend = half ? w : wlo;
-      const int buf = job & 1;
-      mbar_wait(&afull_bar[buf], (job >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-      float bm = NEG_INF;
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + c0, v);
-        tmem_ld_wait();
+    // per-key scale  log2(e) d^-1/2 / max(|S_j|, 1e-12)  (F.normalize eps, :58; logits are kept in log2 units)
+    // and per-row bound  log2(e) d^-1/2 |S_j|  on the magnitude of row j's logits
+    auto key_scales = [&](int item, int par) {
+      const int b_ = item / pairs_per_img, l_ = (item % pairs_per_img) / p.npairs;
+      for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS) {
+        float v = 0.f, bd = 0.f;
+        if (j < p.n) {
+          const float* ns = p.nsq + (((size_t)b_ * p.n + j) * p.L + l_) * p.nparts;
+          float ss = 0.f;
+          if ((p.nparts & 3) == 0 && p.nparts <= 16) {      // one round trip: all partials in flight, then summed in order
+            float4 q[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bm = fmaxf(bm, logit(v[i], kb * 256 + c0 + i));
-      }
-      red[(kb & 1) * 256 + half * 128 + t] = bm;                     // exchange the block max with the other half
-      named_bar_sync(2 + quad, 64);
-      bm = fmaxf(bm, red[(kb & 1) * 256 + (half ^ 1) * 128 + t]);
-      const float m_new = fmaxf(m_run, bm);
-      const float m_safe = (m_new == NEG_INF) ? 0.f : m_new;
-      l_run *= (m_run == NEG_INF) ? 0.f : ex2_approx((m_run - m_safe) * LOG2E);
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[8];
+            for (int i = 0; i < 4; ++i)
+              q[i] = 4 * i < p.nparts ? __ldg(reinterpret_cast<const float4*>(ns) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float e0 = ex2_approx((logit(v[i], kb * 256 + c0 + i) - m_safe) * LOG2E);
-          const float e1 = ex2_approx((logit(v[i + 1], kb * 256 + c0 + i + 1) - m_safe) * LOG2E);
-          l_run += e0 + e1;
-          pk[i / 2] = pack_bf16x2(e0, e1);
+            for (int i = 0; i < 4; ++i) ss = (((ss + q[i].x) + q[i].y) + q[i].z) + q[i].w;
+          } else {
+            for (int i = 0; i < p.nparts; ++i) ss += ns[i];
+          }
+          const float nrm = sqrtf(ss);
+          v = p.scale * LOG2E / fmaxf(nrm, 1e-12f);
+          bd = p.scale * LOG2E * nrm;
         }
-        const int key = kb * 256 + c0;                     // multiple of 16
-        uint8_t* rowp = p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128;
-        const int ch = (key & 63) >> 3;                    // 16-byte chunk index inside the 128-byte row (even)
-        *reinterpret_cast<uint4*>(rowp + (((ch) ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (t & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        rs[par * p.n_pad16 + j] = v;
+        bnd[par * p.n_pad16 + j] = bd;
       }
-      m_used[kb] = m_safe;
-      m_run = m_new;
-      tc_fence_before_sync();
-      mbar_arrive(&aempty_bar[buf]);
-    }
-    const float m_fin = (m_run == NEG_INF) ? 0.f : m_run;
-    // bring every block's probabilities onto the final stabiliser; zero the K-padding keys
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      if (m_used[kb] == m_fin) continue;
-      const float f = ex2_approx((m_used[kb] - m_fin) * LOG2E);
-      const int w = min(256, p.n_pad16 - kb * 256);
-      const int wlo = ((w >> 5) + ((w >> 4) & 1)) << 4;
-      const int cbeg = half ? wlo : 0, cend = half ? w : wlo;
-      for (int c0 = cbeg; c0 < cend; c0 += 8) {
-        const int key = kb * 256 + c0;
-        uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
-                                              ((((key & 63) >> 3) ^ (t & 7)) << 4));
-        uint4 u = *ptr;
-        uint32_t wv[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float lo = __uint_as_float(wv[i] << 16) * f, hi = __uint_as_float(wv[i] & 0xFFFF0000u) * f;
-          wv[i] = pack_bf16x2(lo, hi);
-        }
-        *ptr = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-      }
-    }
-    if (half == 1) {
+    };
+    if (cluster_id < p.num_items) key_scales(cluster_id, 0);
+    // key coordinates for the careful path: padding keys sit 20000 rows away, so one distance test masks them as well
+    // (:67-69; without a radius every real key is at (0, 0), the query at (0, 0) and the threshold 1)
+    for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS)
+      key_hw[j] = j >= p.n ? (20000u << 16) : use_mask ? ((uint32_t)(j / p.mask_side) << 16) | (uint32_t)(j % p.mask_side) : 0u;
+    const int d2_max = use_mask ? p.mask_d2_max : 1;
+    if (part == 3) {                          // K-padding keys of the last 64-key chunk: P = 0, never written again
       for (int key = p.n_pad16; key < p.n_pad64; key += 8) {
         uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
                                               ((((key & 63) >> 3) ^ (t & 7)) << 4));
         *ptr = make_uint4(0, 0, 0, 0);
       }
     }
-    red[512 + half * 128 + t] = l_run;                                 // row sum = sum of both halves
-    fence_proxy_async_smem();
-    mbar_arrive(pready_bar);
-    named_bar_sync(2 + quad, 64);
-    const float inv_l = 1.0f / (l_run + red[512 + (half ^ 1) * 128 + t]);
 
-    // output: O slice (128 x <=256) from TMEM, scaled by 1/rowsum, bf16, transposed through a 2 KB patch
-    // (in the Q area of pipeline stage 0, idle in phase 2) so that stores cover 64-byte row segments
-    uint8_t* patch = stages + (size_t)warp * 2048;
-    const int rows_left = p.n - (q0 + quad * 32);
-    for (int ps = 0; ps < npass; ++ps, ++job) {
-      const int wd = min(256, p.d - ps * 256);
-      const int hw = ((wd >> 6) + ((wd >> 5) & 1)) << 5;              // columns of half 0 (multiple of 32)
-      const int cbeg = half ? hw : 0, cend = half ? wd : hw;
-      const int buf = job & 1;
-      mbar_wait(&afull_bar[buf], (job >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-      __nv_bfloat16* cdst = p.c_out + ((img_row0 + q0 + quad * 32) * p.L + l) * p.d + ps * 256;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
+    uint32_t job = 0;
+    int item_par = 0;
+    for (int it = cluster_id; it < p.num_items; it += num_clusters, item_par ^= 1) {
+      const int b = it / pairs_per_img, l = (it % pairs_per_img) / p.npairs;
+      const int q0 = (2 * (it % p.npairs) + (int)cta_rank) * BM;
+      const int qi = q0 + t;
+      const size_t img_row0 = (size_t)b * p.n;
+      const float* rsc = rs + item_par * p.n_pad16;
+      named_bar_sync(1, ATTN_SM_THREADS);      // this item's key scales are visible
+
+      const int qh = use_mask ? qi / p.mask_side : 0, qw = use_mask ? qi % p.mask_side : 0;
+      const int diag = p.attend_self ? -1 : qi;
+      const int diag_blk = p.attend_self ? -1 : (q0 + quad * 32) >> 5;      // the 32 keys holding this warp's diagonals
+      // logits (log2 units) of 16 keys starting at j0 (multiple of 16).  Plain blocks - no diagonal, padding or
+      // radius mask, a warp-uniform property - take one multiply per key; the others a branch-free select chain.
+      auto plain = [&](int j0) -> bool { return !use_mask && j0 + 16 <= p.n && (j0 >> 5) != diag_blk; };
+      auto logits16 = [&](const uint32_t (&v)[16], int j0, float (&lg)[16]) {
+        const float4* r4 = reinterpret_cast<const float4*>(rsc + j0);
+        if (plain(j0)) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(
-              pack_bf16x2(__uint_as_float(v[8 * c + 0]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
-              pack_bf16x2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
-              pack_bf16x2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
-              pack_bf16x2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
-        __syncwarp();
-        const int c = lane & 3;
+          for (int q = 0; q < 4; ++q) {
+            const float4 r = r4[q];
+            lg[4 * q] = __uint_as_float(v[4 * q]) * r.x;         lg[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * r.y;
+            lg[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * r.z; lg[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * r.w;
+          }
+        } else {
+          const uint4* h4 = reinterpret_cast<const uint4*>(key_hw + j0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + (lane >> 2);
-          const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-          if (r < rows_left) *reinterpret_cast<uint4*>(cdst + (size_t)r * p.L * p.d + c0 + c * 8) = val;
+          for (int q = 0; q < 4; ++q) {
+            const float4 r = r4[q];
+            const uint4 h = h4[q];
+            const float rr[4] = {r.x, r.y, r.z, r.w};
+            const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j0 + 4 * q + e;
+              float sv = __uint_as_float(v[4 * q + e]) * rr[e];                       // (:60)
+              sv = (j == diag) ? -5e-4f * LOG2E : sv;                                 // (:62-65)
+              const int dh = qh - (int)(hh[e] >> 16), dw = qw - (int)(hh[e] & 0xFFFFu);
+              lg[4 * q + e] = (dh * dh + dw * dw > d2_max) ? NEG_INF : sv;            // (:67-69) and key padding
+            }
+          }
         }
+      };
+
+      // stabiliser: the row's logit bound, or (beyond 2^BOUND_MAX, decided per warp) the exact running maximum
+      const float row_bound = qi < p.n ? bnd[item_par * p.n_pad16 + qi] : 0.f;
+      const bool exact_max = __any_sync(0xffffffffu, !(row_bound <= ATTN_BOUND_MAX));
+      float m_run = exact_max ? NEG_INF : row_bound, l_run = 0.f;      // l_run: this warp's column part only
+      float m_used[ATTN_MAX_KB];
+      for (int kb = 0; kb < p.nkb; ++kb, ++job) {
+        const int w = min(256, p.n_pad16 - kb * 256);
+        const int cbeg = (((w >> 4) * part) >> 2) << 4, cend = (((w >> 4) * (part + 1)) >> 2) << 4;   // 16-key blocks
+        const uint32_t buf = job & 1;
+        mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u;
+        // S is read from TMEM 16 columns at a time; the loops stay rolled (one copy of the block body each)
+        uint32_t cur[16];
+        float lg[16];
+        float m_safe = m_run;
+        if (exact_max) {
+          float bm = NEG_INF;
+#pragma unroll 1
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            tmem_ld16(t_addr + c0, cur);
+            tmem_ld_wait();
+            logits16(cur, kb * 256 + c0, lg);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) bm = fmaxf(bm, fmaxf(fmaxf(lg[i], lg[i + 1]), fmaxf(lg[i + 2], lg[i + 3])));
+          }
+          red[(kb & 1) * 512 + part * 128 + t] = bm;                     // exchange the block max with the other parts
+          named_bar_sync(2 + quad, 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bm = fmaxf(bm, red[(kb & 1) * 512 + q * 128 + t]);
+          const float m_new = fmaxf(m_run, bm);
+          m_safe = (m_new == NEG_INF) ? 0.f : m_new;
+          l_run *= (m_run == NEG_INF) ? 0.f : ex2_approx(m_run - m_safe);
+          m_run = m_new;
+        }
+        // unnormalised probabilities 2^(logit - m) -> bf16 P (UMMA A-operand layout) and their running sum
+        uint32_t nxt[16];
+        if (cbeg < cend) tmem_ld16(t_addr + cbeg, nxt);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+          if (c0 + 16 < cend) tmem_ld16(t_addr + c0 + 16, nxt);      // in flight while this block is processed
+          const int j0 = kb * 256 + c0;
+          logits16(cur, j0, lg);
+          uint32_t pk[8];
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float e0 = ex2_approx(lg[i] - m_safe), e1 = ex2_approx(lg[i + 1] - m_safe);
+            const float e2 = ex2_approx(lg[i + 2] - m_safe), e3 = ex2_approx(lg[i + 3] - m_safe);
+            acc += (e0 + e1) + (e2 + e3);
+            pk[i / 2] = pack_bf16x2(e0, e1);
+            pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          l_run += acc;
+          uint8_t* rowp = p_smem + (size_t)(j0 >> 6) * A_STAGE_BYTES + (size_t)t * 128;
+          const int ch = (j0 & 63) >> 3;                     // 16-byte chunk index inside the 128-byte row (even)
+          *reinterpret_cast<uint4*>(rowp + (((ch) ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (t & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        m_used[kb] = m_safe;
+        tc_fence_before_sync();
         __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(aempty_remote + 8u * buf);
       }
-      tc_fence_before_sync();
-      mbar_arrive(&aempty_bar[buf]);
+      if (exact_max) {
+        const float m_fin = (m_run == NEG_INF) ? 0.f : m_run;
+        // bring every block's probabilities onto the final stabiliser
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (m_used[kb] == m_fin) continue;
+          const float f = ex2_approx(m_used[kb] - m_fin);
+          const int w = min(256, p.n_pad16 - kb * 256);
+          const int cbeg = (((w >> 4) * part) >> 2) << 4, cend = (((w >> 4) * (part + 1)) >> 2) << 4;
+          for (int c0 = cbeg; c0 < cend; c0 += 8) {
+            const int key = kb * 256 + c0;
+            uint4* ptr = reinterpret_cast<uint4*>(p_smem + (size_t)(key >> 6) * A_STAGE_BYTES + (size_t)t * 128 +
+                                                  ((((key & 63) >> 3) ^ (t & 7)) << 4));
+            uint4 u = *ptr;
+            uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = __uint_as_float(wv[i] << 16) * f, hi = __uint_as_float(wv[i] & 0xFFFF0000u) * f;
+              wv[i] = pack_bf16x2(lo, hi);
+            }
+            *ptr = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        }
+      }
+      red[1024 + part * 128 + t] = l_run;                                // row sum = sum of the four parts
+      fence_proxy_async_smem();                // this thread's P rows -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(pready_remote);
+      // while P V runs: key scales of this cluster's next item (other parity; last read in the previous item)
+      if (it + num_clusters < p.num_items) key_scales(it + num_clusters, item_par ^ 1);
+      named_bar_sync(2 + quad, 128);
+      const float inv_l = 1.0f / ((red[1024 + t] + red[1152 + t]) + (red[1280 + t] + red[1408 + t]));
+
+      // output: O slice (128 x <=256) from TMEM, scaled by 1/rowsum, bf16, transposed through a 2 KB patch
+      // so that stores cover 64-byte row segments
+      const int rows_left = p.n - (q0 + quad * 32);
+      for (int sp = 0; sp < nsub; ++sp, ++job) {
+        const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;
+        const int cbeg = part * (wdp >> 2), cend = min(cbeg + (wdp >> 2), p.d - sp * 256);   // columns past d hold zeros
+        const uint32_t buf = job & 1;
+        mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u;
+        __nv_bfloat16* cdst = p.c_out + ((img_row0 + q0 + quad * 32) * p.L + l) * p.d + sp * 256;
+        // 32 columns of this thread's row are scaled by 1/rowsum, rounded to bf16 and transposed through the warp's
+        // 2 KB patch so that stores cover 64-byte row segments
+        auto emit32 = [&](const uint32_t (&v)[32], int c0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(
+                pack_bf16x2(__uint_as_float(v[8 * c + 0]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
+                pack_bf16x2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
+                pack_bf16x2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
+                pack_bf16x2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
+          __syncwarp();
+          const int c = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2);
+            const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+            if (r < rows_left) *reinterpret_cast<uint4*>(cdst + (size_t)r * p.L * p.d + c0 + c * 8) = val;
+          }
+          __syncwarp();
+        };
+        uint32_t cur[32];
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          tmem_ld32(t_addr + c0, cur);
+          tmem_ld_wait();
+          emit32(cur, c0);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(aempty_remote + 8u * buf);
+      }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
   if (warp == W_ALLOC) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -882,19 +1028,23 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     ap.n_pad64 = (n + 63) / 64 * 64;
     ap.nkb = (ap.n_pad16 + 255) / 256;
     ap.nchunk = ap.n_pad64 / 64;
-    ap.kbox_rows = ap.n_pad16 < 256 ? ap.n_pad16 : 256;
+    ap.khalf_rows = (ap.n_pad16 < 256 ? ap.n_pad16 : 256) / 2;
     ap.nparts = g.nparts;
     ap.nsq = b.nsq_in;
     ap.c_out = b.c;
     ap.scale = 1.0f / sqrtf((float)d);
+    const int ntiles = (n + BM - 1) / BM;
+    ap.npairs = (ntiles + 1) / 2;
+    ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
+    ap.num_items = ap.npairs * L * g.B;
     if (ap.nkb > ATTN_MAX_KB) { snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n); return -1; }
-    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + (size_t)ap.n_pad16 * 4 + 768 * 4 + 256;
+    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 + ATTN_RED_FLOATS * 4 + 256;
     const size_t max_smem = 227 * 1024;
     int stages = 4;
-    while (stages > 0 && fixed + (size_t)stages * ATTN_STAGE_BYTES > max_smem) --stages;
+    while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
     if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
     ap.num_stages = stages;
-    const size_t smem = fixed + (size_t)stages * ATTN_STAGE_BYTES;
+    const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
       snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
@@ -903,20 +1053,23 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
     CUtensorMap mq, mk, mv;
     const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
     const uint64_t strides[2] = {(uint64_t)L * d * 2, (uint64_t)n * L * d * 2};
-    const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.kbox_rows, 1},
+    const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.khalf_rows, 1},
                    boxv[3] = {(uint32_t)BK, 64, 1};
     if (!encode_map(enc, &mq, b.sb_in, 3, dims, strides, boxq, err, errlen, "attn.q")) return -3;
     if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
     if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
-    dim3 grid((n + BM - 1) / BM, L, g.B);
+    const int max_clusters = num_sms / 2;
+    const int clusters = ap.num_items < max_clusters ? ap.num_items : max_clusters;
     ProfScope scope(prof, PROF_ATTN, st);
     {
       cudaLaunchConfig_t acfg{};
-      acfg.gridDim = grid; acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
-      cudaLaunchAttribute aattr[1];
-      aattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
-      aattr[0].val.programmaticStreamSerializationAllowed = 1;
-      acfg.attrs = aattr; acfg.numAttrs = 1;
+      acfg.gridDim = dim3(2 * clusters); acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
+      cudaLaunchAttribute aattr[2];
+      aattr[0].id = cudaLaunchAttributeClusterDimension;
+      aattr[0].val.clusterDim.x = 2; aattr[0].val.clusterDim.y = 1; aattr[0].val.clusterDim.z = 1;
+      aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
+      aattr[1].val.programmaticStreamSerializationAllowed = 1;
+      acfg.attrs = aattr; acfg.numAttrs = 2;
       cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
     }
     if (launches) ++*launches;

@@ -208,6 +208,38 @@ def test_shape_edge_cases_against_oracle(spec, precision):
         check_bf16(out, ref, spec)
 
 
+@pytest.mark.parametrize("consensus_self", [True, False])
+def test_large_magnitude_state_takes_the_exact_maximum_softmax(consensus_self):
+    """The bf16 consensus kernel stabilises softmax with the bound |S_i| d^-1/2 on the logits instead of the row
+    maximum; rows whose bound is out of range fall back to the exact-maximum pass.  Levels of rms ~300 (bound ~430 in
+    log2 units) force that path.  With consensus_self the diagonal logit dominates by hundreds of units, softmax is
+    one-hot and the result is well conditioned: standard bf16 tolerance against the oracle.  Without it the attention
+    weights depend on logit differences far below bf16 resolution of the dot products (any bf16 implementation is
+    ill-conditioned there), so only the fp32 engine is held to the oracle and the bf16 one to finiteness + scale."""
+    dim, L, isz, p = 128, 3, 16, 2                       # n = 64 columns
+    params = O.synth_params(dim, L, isz, p, seed=11)
+    rng = np.random.default_rng(12)
+    img = rng.standard_normal((2, 3, isz, isz)).astype(np.float32)
+    lv = (rng.standard_normal((2, 64, L, dim)) * 300).astype(np.float32)
+    ref = O.glom_forward(params, img, patch_size=p, iters=2, levels=lv, return_all=True, image_size=isz,
+                         dtype=np.float64, consensus_self=consensus_self)
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        m = G.Glom(dim=dim, levels=L, image_size=isz, patch_size=p, precision=precision, consensus_self=consensus_self)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            outs[precision] = m(torch.from_numpy(img).to(DEV), iters=2, levels=torch.from_numpy(lv).to(DEV),
+                                return_all=True).cpu().numpy()
+    assert np.abs(outs["fp32"] - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.isfinite(outs["bf16"]).all()
+    if consensus_self:
+        check_bf16(outs["bf16"], ref, "large-magnitude, consensus_self")
+    else:
+        rel = np.linalg.norm(outs["bf16"] - ref) / np.linalg.norm(ref)
+        assert rel <= 0.25, rel
+
+
 # ----------------------------------------------------------------------------- BASELINE sizes
 FULL = dict(dim=512, levels=6, image_size=224, patch_size=14)
 
