@@ -986,13 +986,74 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
   return cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, BN>, a0, a1, a2, bm, p);
 }
 
+// K3: consensus attention -> C
+static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st,
+                            int* launches, char* err, size_t errlen, Profiler* prof) {
+  const int d = g.d, L = g.L, n = g.n;
+  AttnParams ap{};
+  ap.n = n; ap.L = L; ap.d = d;
+  ap.attend_self = g.attend_self; ap.mask_side = g.mask_side; ap.mask_d2_max = g.mask_d2_max;
+  ap.n_pad16 = (n + 15) / 16 * 16;
+  ap.n_pad64 = (n + 63) / 64 * 64;
+  ap.nkb = (ap.n_pad16 + 255) / 256;
+  ap.nchunk = ap.n_pad64 / 64;
+  ap.khalf_rows = (ap.n_pad16 < 256 ? ap.n_pad16 : 256) / 2;
+  ap.nparts = g.nparts;
+  ap.nsq = b.nsq_in;
+  ap.c_out = b.c;
+  ap.scale = 1.0f / sqrtf((float)d);
+  const int ntiles = (n + BM - 1) / BM;
+  ap.npairs = (ntiles + 1) / 2;
+  ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
+  ap.num_items = ap.npairs * L * g.B;
+  if (ap.nkb > ATTN_MAX_KB) {
+    snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n);
+    return -1;
+  }
+  const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
+                       ATTN_RED_FLOATS * 4 + 256;
+  const size_t max_smem = 227 * 1024;
+  int stages = 4;
+  while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
+  if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
+  ap.num_stages = stages;
+  const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
+  static SmemOptIn optin;
+  if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+    return -3;
+  }
+  CUtensorMap mq, mk, mv;
+  const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
+  const uint64_t strides[2] = {(uint64_t)L * d * 2, (uint64_t)n * L * d * 2};
+  const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.khalf_rows, 1},
+                 boxv[3] = {(uint32_t)BK, 64, 1};
+  if (!encode_map(enc, &mq, b.sb_in, 3, dims, strides, boxq, err, errlen, "attn.q")) return -3;
+  if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
+  if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
+  const int max_clusters = num_sms / 2;
+  const int clusters = ap.num_items < max_clusters ? ap.num_items : max_clusters;
+  ProfScope scope(prof, PROF_ATTN, st);
+  cudaLaunchConfig_t acfg{};
+  acfg.gridDim = dim3(2 * clusters); acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
+  cudaLaunchAttribute aattr[2];
+  aattr[0].id = cudaLaunchAttributeClusterDimension;
+  aattr[0].val.clusterDim.x = 2; aattr[0].val.clusterDim.y = 1; aattr[0].val.clusterDim.z = 1;
+  aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
+  aattr[1].val.programmaticStreamSerializationAllowed = 1;
+  acfg.attrs = aattr; acfg.numAttrs = 2;
+  const cudaError_t e = cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
+  if (launches) ++*launches;
+  if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
+
 int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
               char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
   // One launch each of K1 (all groups), K3, K2 (all levels).  Splitting K1/K2 into per-level batches so that H stays
   // L2-resident was measured slower (5.3 / 5.6 / 6.5 ms per step for 3 / 2 / 1 levels per batch vs 5.06 ms): the extra
   // kernel boundaries and partial waves cost more than the saved HBM traffic (profiles/README.md).
-  const int level_batch = L;
   CUtensorMap mh;
   const int m128 = (rows + BM - 1) / BM;
   if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
@@ -1002,98 +1063,36 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int nu
   if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
   if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
   if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, (uint32_t)g.bn2 / 2, err, errlen, "W2p")) return -3;
-  bool attn_done = false;
-  for (int l0 = 0; l0 < L; l0 += level_batch) {
-    const int l1 = (l0 + level_batch < L) ? l0 + level_batch : L;
-    // ---------------- K1: grouped GEMM1 + bias + GELU -> H   (groups of levels [l0, l1))
-    {
-      const int g0 = 2 * l0, g1 = (2 * l1 < g.G) ? 2 * l1 : g.G;
-      GemmParams p{};
-      p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-      p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.z0 = g0; p.num_tiles = (g1 - g0) * p.num_m * p.num_n;
-      p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
-      ProfScope scope(prof, PROF_GEMM1, st);
-      cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
-      if (launches) ++*launches;
-      if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
-    }
-    if (!attn_done) {
-      attn_done = true;
-      // ---------------- K3: consensus attention -> C  (after the first K1 so that C is still L2-resident for K2)
+  // ---------------- K1: grouped GEMM1 + bias + GELU -> H   (all 2L-1 groups)
   {
-    AttnParams ap{};
-    ap.n = n; ap.L = L; ap.d = d;
-    ap.attend_self = g.attend_self; ap.mask_side = g.mask_side; ap.mask_d2_max = g.mask_d2_max;
-    ap.n_pad16 = (n + 15) / 16 * 16;
-    ap.n_pad64 = (n + 63) / 64 * 64;
-    ap.nkb = (ap.n_pad16 + 255) / 256;
-    ap.nchunk = ap.n_pad64 / 64;
-    ap.khalf_rows = (ap.n_pad16 < 256 ? ap.n_pad16 : 256) / 2;
-    ap.nparts = g.nparts;
-    ap.nsq = b.nsq_in;
-    ap.c_out = b.c;
-    ap.scale = 1.0f / sqrtf((float)d);
-    const int ntiles = (n + BM - 1) / BM;
-    ap.npairs = (ntiles + 1) / 2;
-    ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
-    ap.num_items = ap.npairs * L * g.B;
-    if (ap.nkb > ATTN_MAX_KB) { snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n); return -1; }
-    const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 + ATTN_RED_FLOATS * 4 + 256;
-    const size_t max_smem = 227 * 1024;
-    int stages = 4;
-    while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
-    if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
-    ap.num_stages = stages;
-    const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
-    static SmemOptIn optin;
-    if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
-      snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
-      return -3;
-    }
-    CUtensorMap mq, mk, mv;
-    const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
-    const uint64_t strides[2] = {(uint64_t)L * d * 2, (uint64_t)n * L * d * 2};
-    const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.khalf_rows, 1},
-                   boxv[3] = {(uint32_t)BK, 64, 1};
-    if (!encode_map(enc, &mq, b.sb_in, 3, dims, strides, boxq, err, errlen, "attn.q")) return -3;
-    if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
-    if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
-    const int max_clusters = num_sms / 2;
-    const int clusters = ap.num_items < max_clusters ? ap.num_items : max_clusters;
-    ProfScope scope(prof, PROF_ATTN, st);
-    {
-      cudaLaunchConfig_t acfg{};
-      acfg.gridDim = dim3(2 * clusters); acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
-      cudaLaunchAttribute aattr[2];
-      aattr[0].id = cudaLaunchAttributeClusterDimension;
-      aattr[0].val.clusterDim.x = 2; aattr[0].val.clusterDim.y = 1; aattr[0].val.clusterDim.z = 1;
-      aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
-      aattr[1].val.programmaticStreamSerializationAllowed = 1;
-      acfg.attrs = aattr; acfg.numAttrs = 2;
-      cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
-    }
+    GemmParams p{};
+    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.z0 = 0; p.num_tiles = g.G * p.num_m * p.num_n;
+    p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
+    ProfScope scope(prof, PROF_GEMM1, st);
+    cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
     if (launches) ++*launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+    if (e != cudaSuccess) { snprintf(err, errlen, "gemm1 launch: %s", cudaGetErrorString(e)); return -3; }
   }
-    }
-    // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)   (levels [l0, l1))
-    {
-      GemmParams p{};
-      p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-      p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.z0 = l0; p.num_tiles = (l1 - l0) * p.num_m * p.num_n;
-      p.n_half = (l1 == L) ? p.num_m * p.num_n : 0;
-      p.m128 = m128;
-      p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
-      p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
-      cudaError_t e;
-      ProfScope scope(prof, PROF_GEMM2, st);
-      if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
-      else if (g.bn2 == 128) e = launch_gemm<1, 128>(mh, mh, mh, mw2, p, num_sms, st);
-      else e = launch_gemm<1, 64>(mh, mh, mh, mw2, p, num_sms, st);
-      if (launches) ++*launches;
-      if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
-    }
+  // ---------------- K3 between K1 and K2 (C is then still L2-resident when K2's epilogue reads it; launching it
+  // first instead measured the same within 0.2 %)
+  if (int rc = launch_attention(g, b, enc, num_sms, st, launches, err, errlen, prof)) return rc;
+  // ---------------- K2: grouped GEMM2 + combine -> state t+1 (+ shadows, norms)   (all levels)
+  {
+    GemmParams p{};
+    p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
+    p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.z0 = 0; p.num_tiles = L * p.num_m * p.num_n;
+    p.n_half = p.num_m * p.num_n;
+    p.m128 = m128;
+    p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+    p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+    cudaError_t e;
+    ProfScope scope(prof, PROF_GEMM2, st);
+    if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
+    else if (g.bn2 == 128) e = launch_gemm<1, 128>(mh, mh, mh, mw2, p, num_sms, st);
+    else e = launch_gemm<1, 64>(mh, mh, mh, mw2, p, num_sms, st);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { snprintf(err, errlen, "gemm2 launch: %s", cudaGetErrorString(e)); return -3; }
   }
   return 0;
 }
