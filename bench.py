@@ -312,36 +312,36 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
 
         # -------- end to end through the public API with host buffers: every step copies its images from pinned
-        # host memory and its result back to pinned host memory inside the timed region.  Copies run on a second
-        # stream, double-buffered, so step i's D2H and step i+1's H2D overlap step i+1's compute.
-        copy_stream = torch.cuda.Stream(dev)
+        # host memory and its result back to pinned host memory inside the timed region.  Copies run on two extra
+        # streams (one per direction), double-buffered, so step i's D2H and step i+2's H2D overlap step i+1's compute.
+        h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)   # one per copy engine / PCIe direction
         host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
 
         def e2e_loop(nsteps):
             staged = None
             ready = torch.cuda.Event()
-            with torch.cuda.stream(copy_stream):
+            with torch.cuda.stream(h2d_stream):
                 staged = host_imgs[0].to(dev, non_blocking=True)
-                ready.record(copy_stream)
+                ready.record(h2d_stream)
             for i in range(nsteps):
                 stream.wait_event(ready)                       # this step's images are on the device
                 x = staged
                 if i + 1 < nsteps:                             # prefetch the next step's images
                     nxt_ready = torch.cuda.Event()
-                    with torch.cuda.stream(copy_stream):
+                    with torch.cuda.stream(h2d_stream):
                         staged = host_imgs[(i + 1) % NBUF].to(dev, non_blocking=True)
-                        nxt_ready.record(copy_stream)
+                        nxt_ready.record(h2d_stream)
                 out = model(x, iters=T)                        # public API call on the compute stream
                 done = torch.cuda.Event()
                 done.record(stream)
                 x.record_stream(stream)
-                with torch.cuda.stream(copy_stream):           # result back to the host
-                    copy_stream.wait_event(done)
+                with torch.cuda.stream(d2h_stream):            # result back to the host
+                    d2h_stream.wait_event(done)
                     host_outs[i % 2].copy_(out, non_blocking=True)
-                    out.record_stream(copy_stream)
+                    out.record_stream(d2h_stream)
                 if i + 1 < nsteps:
                     ready = nxt_ready
-            stream.wait_stream(copy_stream)                    # the last D2H is inside the timed region
+            stream.wait_stream(d2h_stream)                     # the last D2H is inside the timed region
 
         e2e_loop(2)
         barrier()
@@ -441,9 +441,9 @@ def main():
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores = cpu_port_run(4, 3, 3)
+            v, sec, cores = cpu_port_run(4, 3, 5)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
-                                    "sample": f"numpy oracle, same shapes, batch=4 iters=3, median of 3 reps "
+                                    "sample": f"numpy oracle, same shapes, batch=4 iters=3, median of 5 reps "
                                               f"({sec:.2f} s each); BLAS + threaded erf on {cores} cores"}
         print(json.dumps(line), flush=True)
     if distributed:
