@@ -1,0 +1,18 @@
+// How many clusters of size 2 / 4 / 8 (one CTA per SM, ~200 KB dynamic smem) can be co-resident?
+#include <cstdio>
+#include <cuda_runtime.h>
+__global__ void dummy(int* p) { extern __shared__ char s[]; if (p) p[0] = s[0]; }
+int main() {
+  cudaFuncSetAttribute(dummy, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(dummy, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+  printf("SMs %d\n", prop.multiProcessorCount);
+  for (int cs : {1, 2, 4, 8, 16}) {
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(prop.multiProcessorCount / cs * cs); cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1; cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dummy, &cfg);
+    printf("cluster %2d: max active clusters %d (%d SMs) %s\n", cs, n, n * cs, cudaGetErrorString(e));
+  }
+  return 0;
+}
