@@ -96,14 +96,16 @@ static cudaError_t gemm_f32(const GemmF32& q, int batches, cudaStream_t st, int*
 // =====================================================================================
 // element-wise / reduction helpers
 // =====================================================================================
-// g (R, L, d)  <-  gin (R, L, d) / c_l        (:142);   ds (R, L, d) <- g (residual term of the sum, :141)
+// g (R, L, d)  <-  (gin + extra) (R, L, d) / c_l   (:142);   ds (R, L, d) <- g (residual term of the sum, :141)
+// `extra` (nullable) is the upstream gradient of this time step's own output when every step is returned (:147-148)
 __global__ void scale_by_contrib_kernel(size_t total, int L, int d, const float* __restrict__ gin,
-                                        float* __restrict__ g, float* __restrict__ ds) {
+                                        const float* __restrict__ extra, float* __restrict__ g, float* __restrict__ ds) {
   const size_t total4 = total / 4;
   const unsigned d4 = (unsigned)d / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned l = (unsigned)((i / d4) % (unsigned)L);
     float4 v = reinterpret_cast<const float4*>(gin)[i];
+    if (extra) { const float4 e = reinterpret_cast<const float4*>(extra)[i]; v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
     if (l == (unsigned)L - 1) { v.x /= 3.0f; v.y /= 3.0f; v.z /= 3.0f; v.w /= 3.0f; }
     else { v.x *= 0.25f; v.y *= 0.25f; v.z *= 0.25f; v.w *= 0.25f; }
     reinterpret_cast<float4*>(g)[i] = v;
@@ -317,19 +319,18 @@ BackwardLayout backward_layout(const Geometry& g, int precision) {
 // One reverse step: given gin = dL/dS_{t+1}, produce ds = dL/dS_t (without the external grad of slab t) and
 // accumulate parameter / token / pos gradients.
 static cudaError_t backward_step(const Geometry& g, const BackwardArgs& a, const float* s_t, const float* gin,
-                                 char* ws, const BackwardLayout& wl, bool mlp_on_tc, bool attn_on_tc, cudaStream_t st,
-                                 int* launches) {
+                                 const float* gextra, float* ds, char* ws, const BackwardLayout& wl, bool mlp_on_tc,
+                                 bool attn_on_tc, cudaStream_t st, int* launches) {
   const int R = g.rows, L = g.L, d = g.d, n = g.n, h4 = 4 * g.d;
   const long long ld = (long long)L * d;
-  float* gs = reinterpret_cast<float*>(ws + wl.gs_off);       // gin / c
-  float* ds = reinterpret_cast<float*>(ws + wl.ds_off);
+  float* gs = reinterpret_cast<float*>(ws + wl.gs_off);       // (gin + gextra) / c
   float* pre = reinterpret_cast<float*>(ws + wl.pre_off);
   float* hb = reinterpret_cast<float*>(ws + wl.h_off);
   float* dh = reinterpret_cast<float*>(ws + wl.dh_off);
   float* xp = reinterpret_cast<float*>(ws + wl.xp_off);
   float* dx = reinterpret_cast<float*>(ws + wl.dx_off);
   const size_t state = (size_t)R * L * d;
-  scale_by_contrib_kernel<<<nblk(state), 256, 0, st>>>(state, L, d, gin, gs, ds);
+  scale_by_contrib_kernel<<<nblk(state), 256, 0, st>>>(state, L, d, gin, gextra, gs, ds);
   CKL();
 
   // ---- the two grouped MLPs (:23-36), one group at a time (fp32 path; the bf16 engine runs them on tensor cores)
@@ -549,9 +550,9 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
   const bool attn_tc = tc && g.n % 8 == 0;      // TMA row pitch of the (Z, n, n) bf16 buffers must be a multiple of 16 B
   char* ws = static_cast<char*>(workspace);
   const size_t state = (size_t)g.rows * g.L * g.d;
-  float* G = reinterpret_cast<float*>(ws + wl.g_off);
+  // gradient w.r.t. the state walks backwards through two ping-pong slabs: step t reads (gin + gextra) and writes ds
+  float* slab[2] = {reinterpret_cast<float*>(ws + wl.ds_off), reinterpret_cast<float*>(ws + wl.g_off)};
   float* gs = reinterpret_cast<float*>(ws + wl.gs_off);
-  float* ds = reinterpret_cast<float*>(ws + wl.ds_off);
   MlpBwdTc m{};
   if (tc) {
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
@@ -580,11 +581,13 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
       CKI(cudaMemsetAsync(m.dpre, 0, wl.blocked_bytes, st));
     }
   }
-  const float* top = grad_all ? a.grad_out + (size_t)iters * state : a.grad_out;
-  CKI(cudaMemcpyAsync(G, top, state * 4, cudaMemcpyDeviceToDevice, st));
-  for (int t = iters - 1; t >= 0; --t) {
+  // pending upstream gradient of S_{t+1}: gin (+ gextra, the cotangent of that step's own output under return_all)
+  const float* gin = grad_all ? a.grad_out + (size_t)iters * state : a.grad_out;
+  const float* gextra = nullptr;
+  for (int t = iters - 1, k = 0; t >= 0; --t, ++k) {
     const float* s_t = a.states + (size_t)t * state;
-    CKI(backward_step(g, a, s_t, G, ws, wl, tc, attn_tc, st, launches));   // scale (+ the fp32 MLP / attention backward)
+    float* ds = slab[k & 1];
+    CKI(backward_step(g, a, s_t, gin, gextra, ds, ws, wl, tc, attn_tc, st, launches));   // scale (+ the fp32 MLP / attention backward)
     if (tc) {
       bwd_shadows_kernel<<<nblk(state / 4), 256, 0, st>>>(g.rows, g.n, g.L, g.d, s_t, gs, a.pos,
                                                           const_cast<__nv_bfloat16*>(m.sb), const_cast<__nv_bfloat16*>(m.sp),
@@ -631,19 +634,20 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
       colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G, 8), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
       CKLI();
     }
-    CKI(cudaMemcpyAsync(G, ds, state * 4, cudaMemcpyDeviceToDevice, st));
-    if (grad_all) {
-      add_kernel<<<nblk(state), 256, 0, st>>>(state, a.grad_out + (size_t)t * state, G);
+    gin = ds;
+    gextra = grad_all ? a.grad_out + (size_t)t * state : nullptr;
+  }
+  // gradient w.r.t. S_0 = gin + gextra
+  for (const float* part : {gin, gextra}) {
+    if (!part) continue;
+    if (a.d_state0) {
+      add_kernel<<<nblk(state), 256, 0, st>>>(state, part, a.d_state0);
       CKLI();
     }
-  }
-  if (a.d_state0) {
-    add_kernel<<<nblk(state), 256, 0, st>>>(state, G, a.d_state0);
-    CKLI();
-  }
-  if (a.d_init) {
-    init_grad_kernel<<<dim3((g.L * g.d + 255) / 256, 64), 256, 0, st>>>(g.rows, g.L, g.d, G, a.d_init);
-    CKLI();
+    if (a.d_init) {
+      init_grad_kernel<<<dim3((g.L * g.d + 255) / 256, 64), 256, 0, st>>>(g.rows, g.L, g.d, part, a.d_init);
+      CKLI();
+    }
   }
   return 0;
 #undef CKI

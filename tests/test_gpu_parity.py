@@ -240,6 +240,42 @@ def test_large_magnitude_state_takes_the_exact_maximum_softmax(consensus_self):
         assert rel <= 0.25, rel
 
 
+def test_cached_workspaces_side_streams_and_cuda_graph_replay_are_bit_stable():
+    """Cross-call persistence: packed weights and workspaces are cached per module; interleaving two
+    models, changing the batch size, running on a side stream and replaying a captured CUDA graph of `forward`
+    (the library never allocates or synchronises) must all reproduce the first results bit for bit."""
+    torch.manual_seed(0)
+    a = G.Glom(dim=256, levels=4, image_size=64, patch_size=8).to(DEV).eval()
+    b = G.Glom(dim=128, levels=3, image_size=32, patch_size=4).to(DEV).eval()
+    with torch.no_grad():
+        xa = [torch.randn(B, 3, 64, 64, device=DEV) for B in (1, 3, 5)]
+        xb = [torch.randn(B, 3, 32, 32, device=DEV) for B in (2, 4)]
+        ra = [a(x, iters=3) for x in xa]
+        rb = [b(x, iters=2) for x in xb]
+        for i in (2, 0, 1):
+            assert torch.equal(a(xa[i], iters=3), ra[i])
+            if i < 2:
+                assert torch.equal(b(xb[i], iters=2), rb[i])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            y = a(xa[1], iters=3)
+        torch.cuda.current_stream().wait_stream(side)
+        assert torch.equal(y, ra[1])
+        static_x = xa[2].clone()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            a(static_x, iters=3)                        # warm-up on a capture-capable stream
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = a(static_x, iters=3)
+        static_x.copy_(xa[0].expand_as(static_x))       # new input, replay
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_y[0], ra[0][0])
+
+
 # ----------------------------------------------------------------------------- BASELINE sizes
 FULL = dict(dim=512, levels=6, image_size=224, patch_size=14)
 
