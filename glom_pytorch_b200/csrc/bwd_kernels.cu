@@ -134,8 +134,10 @@ __global__ void gelu_bwd_kernel(size_t total, const float* __restrict__ pre, flo
   }
 }
 // out[c] += sum_r src[r * row_stride + c]          (bias gradients); grid (cols / 32, row chunks)
+// out2 (nullable) receives the same sums for its first cols2 columns (the top-down second-layer biases see the
+// same upstream gradient as the bottom-up ones on levels 0 .. L-2)
 __global__ void colsum_acc_kernel(int rows, int cols, long long row_stride, const float* __restrict__ src,
-                                  float* __restrict__ out) {
+                                  float* __restrict__ out, float* __restrict__ out2 = nullptr, int cols2 = 0) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5;                 // 8 row slices per block
   const int r_begin = (int)(((long long)rows * blockIdx.y) / gridDim.y), r_end = (int)(((long long)rows * (blockIdx.y + 1)) / gridDim.y);
@@ -150,6 +152,7 @@ __global__ void colsum_acc_kernel(int rows, int cols, long long row_stride, cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
     atomicAdd(out + c, s);
+    if (out2 && c < cols2) atomicAdd(out2 + c, s);
   }
 }
 // dpos[nn, c] += sum_b dx[(b * n + nn), c]          (positional-embedding gradient, :136)
@@ -307,7 +310,6 @@ BackwardLayout backward_layout(const Geometry& g, int precision) {
     w.w1t_off = take((size_t)g.G * 4 * g.d * g.d * 2);
     w.b1p_off = take((size_t)g.G * 4 * g.d * 4);
     w.bpre_off = take(w.blocked_bytes); w.bh_off = take(w.blocked_bytes); w.bdpre_off = take(w.blocked_bytes);
-    w.dxall_off = take((size_t)g.rows * g.G * g.d * 4);
     w.khatb_off = take((size_t)g.rows * g.L * g.d * 2);
     w.ab_off = take((size_t)g.B * g.L * g.n * g.n * 2);
     w.dsimb_off = take((size_t)g.B * g.L * g.n * g.n * 2);
@@ -482,33 +484,6 @@ __global__ void bwd_shadows_kernel(int rows, int n, int L, int d, const float* _
     }
   }
 }
-// scatter of dx (R, G, d): bottom-up group l -> level l-1 (tokens for l = 0), top-down group l -> level l+1
-__global__ void scatter_dx_kernel(int rows, int L, int d, const float* __restrict__ dx, float* __restrict__ ds,
-                                  float* __restrict__ d_tokens) {
-  const int G = 2 * L - 1;
-  const size_t total = (size_t)rows * d;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / d;
-    const int c = (int)(i % d);
-    const float* src = dx + r * G * d + c;
-    d_tokens[i] += src[0];
-    for (int l = 1; l < L; ++l) ds[(r * L + l - 1) * d + c] += src[(size_t)(2 * l) * d];
-    for (int l = 0; l < L - 1; ++l) ds[(r * L + l + 1) * d + c] += src[(size_t)(2 * l + 1) * d];
-  }
-}
-// d_pos[nn, c] += sum over images and top-down groups of dx
-__global__ void pos_grad_all_kernel(int B, int n, int L, int d, const float* __restrict__ dx, float* __restrict__ dpos) {
-  const int G = 2 * L - 1;
-  const size_t total = (size_t)n * d;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t nn = i / d;
-    const int c = (int)(i % d);
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b)
-      for (int l = 0; l < L - 1; ++l) acc += dx[(((size_t)b * n + nn) * G + 2 * l + 1) * d + c];
-    dpos[i] += acc;
-  }
-}
 // first-layer bias gradients: column sums of the blocked bf16 dpre (G, m128, 4d/64, 128, 64)
 // grid (4d/64, G, row chunks); thread = (8-column group, row lane): 16-byte loads along the 128-byte block rows
 __global__ void colsum_blocked_kernel(int rows, int m128, int d, int L, const __nv_bfloat16* __restrict__ dpre,
@@ -567,7 +542,7 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
     m.pre = reinterpret_cast<__nv_bfloat16*>(ws + wl.bpre_off);
     m.h = reinterpret_cast<__nv_bfloat16*>(ws + wl.bh_off);
     m.dpre = reinterpret_cast<__nv_bfloat16*>(ws + wl.bdpre_off);
-    m.dx = reinterpret_cast<float*>(ws + wl.dxall_off);
+    m.d_tokens = a.d_tokens; m.d_pos = a.d_pos;
     m.d_bu_w1 = a.d_bu_w1; m.d_bu_w2 = a.d_bu_w2; m.d_td_w1 = a.d_td_w1; m.d_td_w2 = a.d_td_w2;
     pack_bwd_weights_kernel<<<148 * 8, 256, 0, st>>>(g.d, g.L, a.bu_w1, a.bu_b1, a.bu_w2, a.td_w1, a.td_b1, a.td_w2,
                                                      const_cast<__nv_bfloat16*>(m.w1p), const_cast<__nv_bfloat16*>(m.w2t),
@@ -622,14 +597,10 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
         normalize_bwd_kernel<<<wblocks, 256, 0, st>>>(g.rows * g.L, d, khat, dkhat, rnorm, ds);
         CKLI();
       }
+      m.ds = ds;
       if (int r = mlp_backward_tc(g, m, enc, num_sms, st, launches, err, errlen)) return r;
-      scatter_dx_kernel<<<nblk((size_t)g.rows * g.d), 256, 0, st>>>(g.rows, g.L, g.d, m.dx, ds, a.d_tokens);
-      CKLI();
-      pos_grad_all_kernel<<<nblk((size_t)g.n * g.d), 256, 0, st>>>(g.B, g.n, g.L, g.d, m.dx, a.d_pos);
-      CKLI();
-      colsum_acc_kernel<<<dim3((g.L * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2);
-      CKLI();
-      colsum_acc_kernel<<<dim3(((g.L - 1) * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, (g.L - 1) * g.d, (long long)g.L * g.d, gs, a.d_td_b2);
+      colsum_acc_kernel<<<dim3((g.L * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2,
+                                                                         a.d_td_b2, (g.L - 1) * g.d);
       CKLI();
       colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G, 8), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
       CKLI();

@@ -132,7 +132,7 @@ struct BackwardLayout {
   size_t g_off, gs_off, ds_off, khat_off, dkhat_off, rnorm_off, pre_off, h_off, dh_off, xp_off, dx_off, attn_off,
       dattn_off;
   // bf16 (tensor-core) MLP backward only
-  size_t xb_off, sb_off, sp_off, gsb_off, w1p_off, w2t_off, w1t_off, b1p_off, bpre_off, bh_off, bdpre_off, dxall_off;
+  size_t xb_off, sb_off, sp_off, gsb_off, w1p_off, w2t_off, w1t_off, b1p_off, bpre_off, bh_off, bdpre_off;
   size_t khatb_off, ab_off, dsimb_off;     // bf16 khat (state-like), probabilities and scaled dsim (Z, n, n)
   size_t blocked_bytes;
   size_t total;
@@ -143,7 +143,8 @@ struct MlpBwdTc {
   const __nv_bfloat16 *w1p, *w2t, *w1t;        // (G*4d, d), (G*4d, d) = W2^T, (G*d, 4d) = W1^T, groups interleaved bu/td
   const float* b1p;                            // (G*4d)
   __nv_bfloat16 *pre, *h, *dpre;               // blocked (G, R_pad/128, 4d/64, 128, 64)
-  float* dx;                                   // (R, G, d)
+  float *ds, *d_tokens, *d_pos;                // input gradients of the groups are reduced straight into these:
+                                               // dL/dS_t (R, L, d), dL/dtokens (R, d), dL/dpos (n, d)
   float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
 };
 int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,

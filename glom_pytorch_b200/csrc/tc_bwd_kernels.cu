@@ -38,7 +38,8 @@ struct BwdParams {
   __nv_bfloat16* pre;
   __nv_bfloat16* h;
   __nv_bfloat16* dpre;
-  float* dx;           // (R, G, d) fp32
+  float *ds, *d_tokens, *d_pos;   // BW_DX reduces dx of group g into dL/dS_t level l-1 (bottom-up l; tokens for l = 0) or
+                                  // l+1 (top-down l, which also feeds dL/dpos, :136)
   // weight gradients in the reference layout (accumulated into)
   float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
   // BW_BATCH: C[z] (M = n rows, N cols) (+)= A[z] . B[z]^T-like, z = (image, level); operands come from 3-D tensor
@@ -286,7 +287,18 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
               }
             }
           } else if (MODE == BW_DX) {
-            if (row < p.rows) *reinterpret_cast<float4*>(p.dx + ((size_t)row * p.G + t.g) * p.d + col) = acc;
+            if (row < p.rows) {
+              // several groups (and, for pos, all images) add into the same element: reduce in L2, no dx round trip
+              const int lg = t.g >> 1;
+              if (t.g == 0) {
+                red_add_f32x4(p.d_tokens + (size_t)row * p.d + col, acc);
+              } else if (t.g & 1) {
+                red_add_f32x4(p.ds + ((size_t)row * p.L + lg + 1) * p.d + col, acc);
+                red_add_f32x4(p.d_pos + (size_t)(row % p.n) * p.d + col, acc);
+              } else {
+                red_add_f32x4(p.ds + ((size_t)row * p.L + lg - 1) * p.d + col, acc);
+              }
+            }
           } else if (MODE == BW_BATCH) {
             const int z = t.g;
             if (row < p.n && col < p.bN) {
@@ -434,7 +446,7 @@ int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int
   if (!ok) return -3;
   BwdParams p{};
   p.rows = rows; p.d = d; p.L = L; p.n = g.n; p.G = G; p.m128 = m128;
-  p.b1p = a.b1p; p.pre = a.pre; p.h = a.h; p.dpre = a.dpre; p.dx = a.dx;
+  p.b1p = a.b1p; p.pre = a.pre; p.h = a.h; p.dpre = a.dpre; p.ds = a.ds; p.d_tokens = a.d_tokens; p.d_pos = a.d_pos;
   p.d_bu_w1 = a.d_bu_w1; p.d_bu_w2 = a.d_bu_w2; p.d_td_w1 = a.d_td_w1; p.d_td_w2 = a.d_td_w2;
   const int nm = (rows + 255) / 256;
   cudaError_t e;
