@@ -94,7 +94,16 @@ __device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) 
   q = fmaf(q, t, -0.9999995827674866f);
   const float tail = ex2_approx(q);                  // Phi(-|x|)
   cdf = x >= 0.f ? 1.0f - tail : tail;
-  pdf = 0.3989422804014327f * ex2_approx(-0.7213475204444817f * x * x);
+  // phi(t) = Phi(-t) * hazard(t): the hazard function is smooth, a degree-6 fit on [0, 6] is good to 2.4e-5 relative,
+  // and the epilogue (XU-bound: ex2 + bf16 packing) saves its second ex2 per element
+  float hz = 7.497369551856536e-06f;
+  hz = fmaf(hz, t, -0.00023059015802573413f);
+  hz = fmaf(hz, t, 0.003048981074243784f);
+  hz = fmaf(hz, t, -0.023022783920168877f);
+  hz = fmaf(hz, t, 0.11135400831699371f);
+  hz = fmaf(hz, t, 0.6360868811607361f);
+  hz = fmaf(hz, t, 0.7979033589363098f);
+  pdf = tail * hz;
 }
 
 template <int MODE>
@@ -240,15 +249,37 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
         for (int i = threadIdx.x; i < BN; i += EPI_WARPS * 32) bias_s[i] = __ldg(p.b1p + (size_t)t.g * 4 * p.d + t.n_blk * BN + i);
         named_bar_sync(1, EPI_WARPS * 32);
       }
+      const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;      // output row band of this warp
+      // blocked address of this lane's 4 values of row r, chunk c0: block (g, row / 128, col / 64), row % 128, col % 64
+      auto blocked_off = [&](int r, int c0) -> size_t {
+        const int row = row0 + r, col = t.n_blk * BN + part * PART_COLS + c0 + c * 4;
+        return ((size_t)((t.g * p.m128 + (row >> 7)) * kbg_n + (col >> 6)) * BM + (row & 127)) * BK + (col & 63);
+      };
+      // BW_DH: gelu'(pre) of the next 32-column chunk is fetched one chunk ahead (the first one before the accumulator
+      // is even complete), so its L2 / HBM latency is off the epilogue's critical path
+      uint2 gp_next[8];
+      auto fetch_gp = [&](int c0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rsub;
+          gp_next[i] = row0 + r < p.rows ? __ldg(reinterpret_cast<const uint2*>(p.pre + blocked_off(r, c0))) : make_uint2(0u, 0u);
+        }
+      };
+      if (MODE == BW_DH) fetch_gp(0);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
-      const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;      // output row band of this warp
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
 #pragma unroll 1
       for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
+        uint2 gp_cur[8];
+        if (MODE == BW_DH) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gp_cur[i] = gp_next[i];
+          if (c0 + 32 < PART_COLS) fetch_gp(c0 + 32);
+        }
         // accumulator chunk -> patch (f32 rows of 128 B, chunk j of row r at j ^ (r & 7)) -> 4 columns x 8 rows per lane
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -263,8 +294,7 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
           const int row = row0 + r;
           if (MODE == BW_PRE || MODE == BW_DH) {
             if (row < p.rows) {
-              // blocked address: block (g, row / 128, col / 64), row % 128, col % 64
-              const size_t off = ((size_t)((t.g * p.m128 + (row >> 7)) * kbg_n + (col >> 6)) * BM + (row & 127)) * BK + (col & 63);
+              const size_t off = blocked_off(r, c0);
               if (MODE == BW_PRE) {
                 // pre-activation -> h = gelu(pre) and gp = gelu'(pre), both bf16 (the `pre` buffer holds gp)
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + part * PART_COLS + c0 + c * 4);
@@ -280,7 +310,7 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
                 *reinterpret_cast<uint2*>(p.h + off) = make_uint2(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]));
                 *reinterpret_cast<uint2*>(p.pre + off) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
               } else {
-                const uint2 pw = *reinterpret_cast<const uint2*>(p.pre + off);       // gelu'(pre)
+                const uint2 pw = gp_cur[i];                                           // gelu'(pre)
                 *reinterpret_cast<uint2*>(p.dpre + off) =
                     make_uint2(pack_bf16x2(acc.x * __uint_as_float(pw.x << 16), acc.y * __uint_as_float(pw.x & 0xFFFF0000u)),
                                pack_bf16x2(acc.z * __uint_as_float(pw.y << 16), acc.w * __uint_as_float(pw.y & 0xFFFF0000u)));
