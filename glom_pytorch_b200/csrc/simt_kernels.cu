@@ -276,9 +276,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(SgemmParams q) {
 // fp32 consensus attention (glom_pytorch.py:56-73).  Block = (image b, level l, 16 queries).
 // =====================================================================================
 constexpr int AQ = 16;
+__device__ __forceinline__ void store_consensus(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_consensus(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+// OutT = float: the fp32 engine.  OutT = bf16: the bf16 engine's path for more columns than the tensor-core kernel
+// holds in shared memory (fp32 arithmetic on the fp32 master state, consensus rounded once to bf16 for K2).
+template <typename OutT>
 __global__ void __launch_bounds__(256) attn_f32_kernel(int n, int L, int d, int attend_self, int mask_side,
                                                        int mask_d2_max, const float* __restrict__ s,
-                                                       float* __restrict__ out) {
+                                                       OutT* __restrict__ out) {
   extern __shared__ float sm[];
   float* qs = sm;                 // [AQ][d]
   float* sim = sm + AQ * d;       // [AQ][n]
@@ -353,24 +358,34 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(int n, int L, int d, int 
     }
 #pragma unroll
     for (int i = 0; i < AQ; ++i)
-      if (q0 + i < n) out[((img + q0 + i) * L + l) * d + c] = acc[i];
+      if (q0 + i < n) store_consensus(out + ((img + q0 + i) * L + l) * d + c, acc[i]);
   }
+}
+
+template <typename OutT>
+static cudaError_t launch_attn_simt(const Geometry& g, const float* s, OutT* c, cudaStream_t st, int* launches) {
+  const size_t smem = (size_t)(AQ * g.d + AQ * g.n) * sizeof(float);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) {
+    cudaError_t e = optin.ensure(attn_f32_kernel<OutT>, smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((g.n + AQ - 1) / AQ, g.L, g.B);
+  attn_f32_kernel<OutT><<<grid, 256, smem, st>>>(g.n, g.L, g.d, g.attend_self, g.mask_side, g.mask_d2_max, s, c);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t attn_simt_bf16_out(const Geometry& g, const float* s32, __nv_bfloat16* c, cudaStream_t st, int* launches) {
+  return launch_attn_simt<__nv_bfloat16>(g, s32, c, st, launches);
 }
 
 cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, int* launches, Profiler* prof) {
   // consensus
   {
     ProfScope scope(prof, PROF_ATTN, st);
-    const size_t smem = (size_t)(AQ * g.d + AQ * g.n) * sizeof(float);
-    static SmemOptIn optin;
-    if (smem > 48 * 1024) {
-      cudaError_t e = optin.ensure(attn_f32_kernel, smem);
-      if (e != cudaSuccess) return e;
-    }
-    dim3 grid((g.n + AQ - 1) / AQ, g.L, g.B);
-    attn_f32_kernel<<<grid, 256, smem, st>>>(g.n, g.L, g.d, g.attend_self, g.mask_side, g.mask_d2_max, b.s_in, b.c);
-    if (launches) ++*launches;
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_attn_simt<float>(g, b.s_in, b.c, st, launches);
     if (e != cudaSuccess) return e;
   }
   SgemmParams q{};

@@ -1006,16 +1006,22 @@ static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiled
   ap.npairs = (ntiles + 1) / 2;
   ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
   ap.num_items = ap.npairs * L * g.B;
-  if (ap.nkb > ATTN_MAX_KB) {
-    snprintf(err, errlen, "bf16 consensus supports n <= %d columns (got %d)", 256 * ATTN_MAX_KB, n);
-    return -1;
-  }
   const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
                        ATTN_RED_FLOATS * 4 + 256;
   const size_t max_smem = 227 * 1024;
   int stages = 4;
   while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
-  if (stages < 1) { snprintf(err, errlen, "bf16 consensus: n = %d columns does not fit shared memory", n); return -1; }
+  if (stages < 1 || ap.nkb > ATTN_MAX_KB) {
+    // more columns than the probabilities of a 128-query tile fit in shared memory (n > 576): the consensus of this
+    // step runs on CUDA cores in fp32 from the master state (correct for any n that the fp32 engine accepts, far slower)
+    ProfScope scope(prof, PROF_ATTN, st);
+    const cudaError_t e = attn_simt_bf16_out(g, b.s32_in, b.c, st, launches);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "consensus for n = %d columns (CUDA-core path): %s", n, cudaGetErrorString(e));
+      return e == cudaErrorInvalidValue ? -1 : -3;
+    }
+    return 0;
+  }
   ap.num_stages = stages;
   const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
   static SmemOptIn optin;
