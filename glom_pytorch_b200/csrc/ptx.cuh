@@ -16,7 +16,6 @@ namespace glom {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -28,9 +27,6 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -96,20 +92,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 // fire-and-forget vector atomic add to global memory (no return value: the reduction happens in L2)
 __device__ __forceinline__ void red_add_f32x4(float* dst, float4 v) {
@@ -117,16 +99,7 @@ __device__ __forceinline__ void red_add_f32x4(float* dst, float4 v) {
                : "memory");
 }
 
-// ---------------------------------------------------------------- TMEM
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
+// ---------------------------------------------------------------- TMEM (allocation: see the CTA-pair section)
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t).
@@ -152,7 +125,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-// ---------------------------------------------------------------- UMMA (tcgen05.mma, cta_group::1, kind::f16)
+// ---------------------------------------------------------------- UMMA descriptors (tcgen05.mma, kind::f16)
 // Shared-memory matrix descriptor, 128-byte swizzle.  start address / LBO / SBO are encoded >> 4.
 //   K-major operand  (rows x 64 bf16, 128 B per row):   SBO = 1024 (8 rows), LBO unused (canonical 1)
 //   MN-major operand (64 bf16 of MN contiguous per K row): LBO = bytes between 64-wide MN blocks,
@@ -171,21 +144,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Arrive on an mbarrier when all previously issued MMAs of this thread have completed
-// (implies tcgen05.fence::before_thread_sync).
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2, cluster of 2)
@@ -261,7 +219,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -275,22 +232,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// 0.5*x*(1+erf(x/sqrt2)) = relu(x) - |x| * Phi(-|x|), with Phi(-a) = 2^p(a) and p a degree-6
-// minimax fit of log2(0.5*erfc(a/sqrt2)) on [0,6] (|gelu error| <= 5e-7 absolute, below fp32
-// rounding of the result; fitted in the build container with numpy against scipy erfc).
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float a = fabsf(x);
-  const float t = fminf(a, 6.0f);
-  float p = 3.290448512416333e-05f;
-  p = fmaf(p, t, -0.0007621519616805017f);
-  p = fmaf(p, t, 0.008038812316954136f);
-  p = fmaf(p, t, -0.05331535264849663f);
-  p = fmaf(p, t, -0.45887142419815063f);
-  p = fmaf(p, t, -1.1511567831039429f);
-  p = fmaf(p, t, -0.9999995827674866f);
-  const float e = ex2_approx(p);
-  return fmaf(-a, e, fmaxf(x, 0.0f));
-}
 
 // Packed-pair version for the GEMM1 epilogue (FFMA2 / FADD2: two fp32 lanes per instruction):
 // gelu(acc + bias) for two neighbouring columns, returned as a bf16x2 word.  Uses u = -|x| (one OR per
