@@ -159,7 +159,9 @@ __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* b
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2);
     const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-    if (FULL || r < rows_left) *reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8) = val;
+    // streaming (evict-first) stores: H (369 MB per step) never fits L2, and letting it through the normal policy
+    // evicts the state shadows and weights the GEMMs and the consensus kernel re-read (measured: K1 -4 %)
+    if (FULL || r < rows_left) __stcs(reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8), val);
   }
   __syncwarp();
 }
