@@ -590,9 +590,9 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
         if (int r = attn_bwd_gemm_tc(g, m.gsb, 1, 0, m.sb, 1, 0, n, d, 0, dA, enc, num_sms, st, launches, err, errlen)) return r;
         attn_softmax_bwd_kernel<<<rblocks, 256, 0, st>>>(Z, n, g.attend_self, g.mask_side, g.mask_d2_max, A, dA, scale, dsim_b);
         CKLI();
-        // dV: ds += A^T dC ;  dQ: ds += (scale dsim) Khat ;  dKhat = (scale dsim)^T Q
-        if (int r = attn_bwd_gemm_tc(g, a_b, 0, 1, m.gsb, 1, 1, d, n, 1, ds, enc, num_sms, st, launches, err, errlen)) return r;
-        if (int r = attn_bwd_gemm_tc(g, dsim_b, 0, 0, khat_b, 1, 1, d, n, 1, ds, enc, num_sms, st, launches, err, errlen)) return r;
+        // dV and dQ in one K-concatenated product: ds += [A^T | scale dsim] [dC ; Khat] ;  dKhat = (scale dsim)^T Q
+        if (int r = attn_bwd_gemm_tc(g, a_b, 0, 1, m.gsb, 1, 1, d, n, 1, ds, enc, num_sms, st, launches, err, errlen,
+                                     dsim_b, 0, 0, khat_b, 1, 1)) return r;
         if (int r = attn_bwd_gemm_tc(g, dsim_b, 0, 1, m.sb, 1, 1, d, n, 2, dkhat, enc, num_sms, st, launches, err, errlen)) return r;
         normalize_bwd_kernel<<<wblocks, 256, 0, st>>>(g.rows * g.L, d, khat, dkhat, rnorm, ds);
         CKLI();

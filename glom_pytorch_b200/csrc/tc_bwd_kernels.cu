@@ -49,6 +49,10 @@ struct BwdParams {
   int a_state, b_state;      // 1: state-like source, 0: attention-like
   int out_kind;              // 0: store (Z, n, n) fp32; 1: accumulate into state-like fp32; 2: store state-like fp32
   float* out;
+  // optional second product accumulated into the same tile (K-concatenation): k blocks >= k_split read the second
+  // operand pair (maps a1 / b1) with its own layout flags; 0 = single product
+  int k_split;
+  int a_mn2, b_mn2, a_state2, b_state2;
 };
 
 struct Tile {
@@ -68,7 +72,7 @@ __device__ __forceinline__ Tile decode(const BwdParams& p, int tile) {
   } else if (MODE == BW_BATCH) {
     const int nm = (p.n + 255) / 256, nn = (p.bN + BN - 1) / BN;
     t.n_blk = tile % nn; t.m_blk = (tile / nn) % nm; t.g = tile / (nn * nm);      // g = problem z
-    t.num_kb = (p.bK + BK - 1) / BK;
+    t.num_kb = p.k_split ? 2 * p.k_split : (p.bK + BK - 1) / BK;
   } else {                                           // weight gradients: 2 * (d/256) * (4d/256) tiles per group
     const int per_kind = (p.d / 256) * (4 * p.d / BN);
     t.g = tile / (2 * per_kind);
@@ -175,13 +179,19 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
             tma_load_2d_2sm(sb, &map_b, bar, kb * BK, t.g * p.d + t.n_blk * BN + (int)cta_rank * (BN / 2));
           } else if (MODE == BW_BATCH) {
             const int z = t.g, bb = z / p.L, lv = z % p.L;
-            const int a_off = p.a_state ? lv * p.d : 0, a_bt = p.a_state ? bb : z;
-            const int b_off = p.b_state ? lv * p.d : 0, b_bt = p.b_state ? bb : z;
+            const bool seg2 = p.k_split && kb >= p.k_split;          // second product of a K-concatenated pair
+            const int kk = seg2 ? kb - p.k_split : kb;
+            const CUtensorMap* am = seg2 ? &map_a1 : &map_a0;
+            const CUtensorMap* bm = seg2 ? &map_b1 : &map_b;
+            const int a_st = seg2 ? p.a_state2 : p.a_state, b_st = seg2 ? p.b_state2 : p.b_state;
+            const int a_mn = seg2 ? p.a_mn2 : p.a_mn, b_mn = seg2 ? p.b_mn2 : p.b_mn;
+            const int a_off = a_st ? lv * p.d : 0, a_bt = a_st ? bb : z;
+            const int b_off = b_st ? lv * p.d : 0, b_bt = b_st ? bb : z;
             const int mrow = t.m_blk * 256 + (int)cta_rank * BM, ncol = t.n_blk * BN + (int)cta_rank * (BN / 2);
-            if (!p.a_mn) tma_load_3d_2sm(sa, &map_a0, bar, a_off + kb * BK, mrow, a_bt);
-            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sa + i * 8192, &map_a0, bar, a_off + mrow + i * 64, kb * BK, a_bt);
-            if (!p.b_mn) tma_load_3d_2sm(sb, &map_b, bar, b_off + kb * BK, ncol, b_bt);
-            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sb + i * 8192, &map_b, bar, b_off + ncol + i * 64, kb * BK, b_bt);
+            if (!a_mn) tma_load_3d_2sm(sa, am, bar, a_off + kk * BK, mrow, a_bt);
+            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sa + i * 8192, am, bar, a_off + mrow + i * 64, kk * BK, a_bt);
+            if (!b_mn) tma_load_3d_2sm(sb, bm, bar, b_off + kk * BK, ncol, b_bt);
+            else for (int i = 0; i < 2; ++i) tma_load_3d_2sm(sb + i * 8192, bm, bar, b_off + ncol + i * 64, kk * BK, b_bt);
           } else {
             // TN: k runs over rows.  A tile = 64 k-rows x this CTA's 128 M-columns, B tile = 64 k-rows x this CTA's
             // 128 N-columns, each as two [64 x 64] boxes (MN-major operand: 128-byte rows of 64 consecutive columns).
@@ -208,9 +218,10 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
     }
   } else if (warp == W_MMA) {
     if (lane == 0 && leader) {
-      const int a_mn = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.a_mn : 0);
-      const int b_mn = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.b_mn : 0);
-      const uint32_t idesc = umma_idesc_bf16(256, BN, a_mn, b_mn);
+      const int a_mn1 = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.a_mn : 0);
+      const int b_mn1 = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.b_mn : 0);
+      const uint32_t idesc1 = umma_idesc_bf16(256, BN, a_mn1, b_mn1);
+      const uint32_t idesc2 = umma_idesc_bf16(256, BN, p.a_mn2, p.b_mn2);      // BW_BATCH with a second product only
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
@@ -223,6 +234,9 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          const bool seg2 = MODE == BW_BATCH && p.k_split && kb >= p.k_split;
+          const int a_mn = seg2 ? p.a_mn2 : a_mn1, b_mn = seg2 ? p.b_mn2 : b_mn1;
+          const uint32_t idesc = seg2 ? idesc2 : idesc1;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // MN-major: 16 k-rows = 2048 B, the two 64-column blocks are 8192 B apart; K-major: 32 B per 16 k
@@ -427,22 +441,28 @@ bool map3d_box(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t inn
 
 // Batched C[z] (n x N) (+)= A[z] B[z] on tensor cores for the attention backward (z = image * L + level).
 //   state-like operands: bf16 (B*n, L*d) tensors; attention-like: bf16 (Z, n, n).  a_mn / b_mn: see BwdParams.
+//   a2_src != nullptr: a second product A2[z] B2[z] of the same shape is accumulated into the same tile (its k blocks
+//   follow the first product's), so both land in `out` with one read-modify-write.
 int attn_bwd_gemm_tc(const Geometry& g, const void* a_src, int a_state, int a_mn, const void* b_src, int b_state, int b_mn,
                      int N, int K, int out_kind, float* out, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
-                     char* err, size_t errlen) {
+                     char* err, size_t errlen, const void* a2_src, int a2_state, int a2_mn, const void* b2_src,
+                     int b2_state, int b2_mn) {
   const int n = g.n, L = g.L, d = g.d, Z = g.B * L;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma2, mb2;
   auto mk = [&](CUtensorMap* m, const void* src, int state, int mn, const char* what) {
     const uint32_t box_rows = mn ? 64u : (uint32_t)BM;
     if (state) return map3d_box(enc, m, src, (uint64_t)L * d, n, g.B, (uint64_t)L * d, (uint64_t)n * L * d, box_rows, err, errlen, what);
     return map3d_box(enc, m, src, n, n, Z, n, (uint64_t)n * n, box_rows, err, errlen, what);
   };
   if (!mk(&ma, a_src, a_state, a_mn, "attn-bwd A") || !mk(&mb, b_src, b_state, b_mn, "attn-bwd B")) return -3;
+  ma2 = ma; mb2 = mb;
+  if (a2_src && (!mk(&ma2, a2_src, a2_state, a2_mn, "attn-bwd A2") || !mk(&mb2, b2_src, b2_state, b2_mn, "attn-bwd B2"))) return -3;
   BwdParams p{};
   p.rows = g.rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
   p.bN = N; p.bK = K; p.a_mn = a_mn; p.b_mn = b_mn; p.a_state = a_state; p.b_state = b_state; p.out_kind = out_kind; p.out = out;
+  if (a2_src) { p.k_split = (K + BK - 1) / BK; p.a_mn2 = a2_mn; p.b_mn2 = b2_mn; p.a_state2 = a2_state; p.b_state2 = b2_state; }
   p.num_tiles = Z * ((n + 255) / 256) * ((N + BN - 1) / BN);
-  cudaError_t e = launch<BW_BATCH>(ma, ma, ma, mb, mb, mb, p, num_sms, st);
+  cudaError_t e = launch<BW_BATCH>(ma, ma2, ma, mb, mb2, mb, p, num_sms, st);
   if (launches) ++*launches;
   if (e != cudaSuccess) { snprintf(err, errlen, "attention-backward gemm launch: %s", cudaGetErrorString(e)); return -3; }
   return 0;
