@@ -484,37 +484,6 @@ __global__ void bwd_shadows_kernel(int rows, int n, int L, int d, const float* _
     }
   }
 }
-// first-layer bias gradients: column sums of the blocked bf16 dpre (G, m128, 4d/64, 128, 64)
-// grid (4d/64, G, row chunks); thread = (8-column group, row lane): 16-byte loads along the 128-byte block rows
-__global__ void colsum_blocked_kernel(int rows, int m128, int d, int L, const __nv_bfloat16* __restrict__ dpre,
-                                      float* __restrict__ d_bu_b1, float* __restrict__ d_td_b1) {
-  const int h = 4 * d, kbg = h / 64;
-  const int g = blockIdx.y, cb = blockIdx.x;
-  const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;        // 8 column groups x 32 row lanes
-  const int r_begin = (int)(((long long)rows * blockIdx.z) / gridDim.z), r_end = (int)(((long long)rows * (blockIdx.z + 1)) / gridDim.z);
-  float acc[8] = {};
-  for (int r = r_begin + rl; r < r_end; r += 32) {
-    const size_t off = ((size_t)((g * m128 + (r >> 7)) * kbg + cb) * 128 + (r & 127)) * 64 + c8 * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(dpre + off);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[2 * i] += __uint_as_float(w[i] << 16);
-      acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  }
-  __shared__ float red[32][65];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[rl][c8 * 8 + i] = acc[i];
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
-    float* dst = (g & 1) ? d_td_b1 : d_bu_b1;
-    atomicAdd(dst + (size_t)(g >> 1) * h + cb * 64 + threadIdx.x, s);
-  }
-}
 
 int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int iters, int grad_all, void* workspace,
                  EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen) {
@@ -544,6 +513,7 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
     m.dpre = reinterpret_cast<__nv_bfloat16*>(ws + wl.bdpre_off);
     m.d_tokens = a.d_tokens; m.d_pos = a.d_pos;
     m.d_bu_w1 = a.d_bu_w1; m.d_bu_w2 = a.d_bu_w2; m.d_td_w1 = a.d_td_w1; m.d_td_w2 = a.d_td_w2;
+    m.d_bu_b1 = a.d_bu_b1; m.d_td_b1 = a.d_td_b1;
     pack_bwd_weights_kernel<<<148 * 8, 256, 0, st>>>(g.d, g.L, a.bu_w1, a.bu_b1, a.bu_w2, a.td_w1, a.td_b1, a.td_w2,
                                                      const_cast<__nv_bfloat16*>(m.w1p), const_cast<__nv_bfloat16*>(m.w2t),
                                                      const_cast<__nv_bfloat16*>(m.w1t), const_cast<float*>(m.b1p));
@@ -601,8 +571,6 @@ int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int it
       if (int r = mlp_backward_tc(g, m, enc, num_sms, st, launches, err, errlen)) return r;
       colsum_acc_kernel<<<dim3((g.L * g.d + 31) / 32, 16), 256, 0, st>>>(g.rows, g.L * g.d, (long long)g.L * g.d, gs, a.d_bu_b2,
                                                                          a.d_td_b2, (g.L - 1) * g.d);
-      CKLI();
-      colsum_blocked_kernel<<<dim3(4 * g.d / 64, g.G, 8), 256, 0, st>>>(g.rows, (g.rows + 127) / 128, g.d, g.L, m.dpre, a.d_bu_b1, a.d_td_b1);
       CKLI();
     }
     gin = ds;

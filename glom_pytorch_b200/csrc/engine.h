@@ -148,6 +148,7 @@ struct MlpBwdTc {
   float *ds, *d_tokens, *d_pos;                // input gradients of the groups are reduced straight into these:
                                                // dL/dS_t (R, L, d), dL/dtokens (R, d), dL/dpos (n, d)
   float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
+  float *d_bu_b1, *d_td_b1;                    // first-layer bias gradients, reduced in the DH epilogue
 };
 int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches,
                     char* err, size_t errlen);

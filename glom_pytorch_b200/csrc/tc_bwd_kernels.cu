@@ -42,6 +42,7 @@ struct BwdParams {
                                   // l+1 (top-down l, which also feeds dL/dpos, :136)
   // weight gradients in the reference layout (accumulated into)
   float *d_bu_w1, *d_bu_w2, *d_td_w1, *d_td_w2;
+  float *d_bu_b1, *d_td_b1;       // first-layer bias gradients (L*4d), ((L-1)*4d): column sums of dpre, reduced by BW_DH
   // BW_BATCH: C[z] (M = n rows, N cols) (+)= A[z] . B[z]^T-like, z = (image, level); operands come from 3-D tensor
   // maps over state-like (R, L*d) tensors (inner offset l*d, batch = image) or attention-like (Z, n, n) ones
   int bN, bK;                // N and K extents
@@ -301,6 +302,7 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
               make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         const int col = t.n_blk * BN + part * PART_COLS + c0 + c * 4;     // output column of this lane's 4 values
+        float colsum[4] = {0.f, 0.f, 0.f, 0.f};                           // BW_DH: first-layer bias gradient partials
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + rsub;
@@ -325,9 +327,10 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
                 *reinterpret_cast<uint2*>(p.pre + off) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
               } else {
                 const uint2 pw = gp_cur[i];                                           // gelu'(pre)
-                *reinterpret_cast<uint2*>(p.dpre + off) =
-                    make_uint2(pack_bf16x2(acc.x * __uint_as_float(pw.x << 16), acc.y * __uint_as_float(pw.x & 0xFFFF0000u)),
-                               pack_bf16x2(acc.z * __uint_as_float(pw.y << 16), acc.w * __uint_as_float(pw.y & 0xFFFF0000u)));
+                const float q0 = acc.x * __uint_as_float(pw.x << 16), q1 = acc.y * __uint_as_float(pw.x & 0xFFFF0000u);
+                const float q2 = acc.z * __uint_as_float(pw.y << 16), q3 = acc.w * __uint_as_float(pw.y & 0xFFFF0000u);
+                colsum[0] += q0; colsum[1] += q1; colsum[2] += q2; colsum[3] += q3;
+                *reinterpret_cast<uint2*>(p.dpre + off) = make_uint2(pack_bf16x2(q0, q1), pack_bf16x2(q2, q3));
               }
             }
           } else if (MODE == BW_DX) {
@@ -370,6 +373,17 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
             old.x += acc.x; old.y += acc.y; old.z += acc.z; old.w += acc.w;
             *reinterpret_cast<float4*>(dst) = old;
           }
+        }
+        if (MODE == BW_DH) {
+          // db1[g, col] += sum over this warp's 32 rows of dpre: the four row sub-lanes of a column group, then L2
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 8);
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 16);
+          }
+          if (rsub == 0)
+            red_add_f32x4(((t.g & 1) ? p.d_td_b1 : p.d_bu_b1) + (size_t)(t.g >> 1) * 4 * p.d + col,
+                          make_float4(colsum[0], colsum[1], colsum[2], colsum[3]));
         }
         __syncwarp();
       }
@@ -498,6 +512,7 @@ int mlp_backward_tc(const Geometry& g, const MlpBwdTc& a, EncodeTiledFn enc, int
   p.rows = rows; p.d = d; p.L = L; p.n = g.n; p.G = G; p.m128 = m128;
   p.b1p = a.b1p; p.pre = a.pre; p.h = a.h; p.dpre = a.dpre; p.ds = a.ds; p.d_tokens = a.d_tokens; p.d_pos = a.d_pos;
   p.d_bu_w1 = a.d_bu_w1; p.d_bu_w2 = a.d_bu_w2; p.d_td_w1 = a.d_td_w1; p.d_td_w2 = a.d_td_w2;
+  p.d_bu_b1 = a.d_bu_b1; p.d_td_b1 = a.d_td_b1;
   const int nm = (rows + 255) / 256;
   cudaError_t e;
   p.num_tiles = G * nm * (4 * d / BN);
