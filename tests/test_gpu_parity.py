@@ -181,6 +181,7 @@ EDGE = [
     (128, 3, 96, 4, (96, 96), 1, 2, {}),                       # n = 576: three key blocks, online max across blocks
     (128, 4, 64, 4, (64, 64), 1, 2, dict(local_consensus_radius=3)),   # radius mask on a 16 x 16 grid (n = 256)
     (64, 2, 8, 4, (8, 8), 1, 3, dict(consensus_self=True)),    # n = 4: a single 16-key block mostly padding
+    (128, 2, 96, 4, (96, 96), 2, 1, dict(local_consensus_radius=2.5, consensus_self=True)),   # n = 576, mask + self, 5 query tiles (odd)
     (64, 2, 64, 2, (64, 64), 1, 2, {}),                        # n = 1024 > 576: consensus on CUDA cores inside the bf16 engine
     (128, 2, 64, 2, (40, 64), 2, 1, dict(local_consensus_radius=0)),   # n = 640 of 1024, same path, two images
 ]
