@@ -519,6 +519,7 @@ struct AttnParams {
   int khalf_rows;                      // rows fetched per K box: half of the (widest) key block
   int num_stages;
   int q_in_k;                          // 1: the CTA's query tile is its half of the single key block
+  int lean;                            // 1: no transpose patches (P of many columns leaves no room): row-per-thread stores
   int npairs, num_items;               // query-tile pairs per (l, b); npairs * L * B
   int nparts;
   const float* nsq;                    // (rows, L, nparts) squared-norm partials of the state
@@ -538,7 +539,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   uint8_t* p_smem = smem;                                                  // nchunk x [128 x 64] bf16, SW128
   uint8_t* stages = p_smem + (size_t)p.nchunk * A_STAGE_BYTES;
   uint8_t* patches = stages + (size_t)p.num_stages * ATTN_SLOT_BYTES;      // 16 x 2 KB transpose patches
-  float* rs = reinterpret_cast<float*>(patches + ATTN_PATCH_BYTES);        // [2][n_pad16] per-key scales, by item parity
+  float* rs = reinterpret_cast<float*>(patches + (p.lean ? 0u : ATTN_PATCH_BYTES));   // [2][n_pad16] per-key scales, by item parity
   float* bnd = rs + 2 * p.n_pad16;                                         // [2][n_pad16] per-row logit bounds
   uint32_t* key_hw = reinterpret_cast<uint32_t*>(bnd + 2 * p.n_pad16);     // [n_pad16] (grid row << 16) | grid column
   float* red = reinterpret_cast<float*>(key_hw + p.n_pad16);               // block maxima (2 parities), row sums
@@ -899,6 +900,19 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         // 32 columns of this thread's row are scaled by 1/rowsum, rounded to bf16 and transposed through the warp's
         // 2 KB patch so that stores cover 64-byte row segments
         auto emit32 = [&](const uint32_t (&v)[32], int c0) {
+          if (p.lean) {        // this thread's own row: 32 columns = 64 contiguous bytes (slower stores, no shared memory)
+            uint4* dst = reinterpret_cast<uint4*>(cdst + (size_t)lane * p.L * p.d + c0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 val = make_uint4(
+                  pack_bf16x2(__uint_as_float(v[8 * c + 0]) * inv_l, __uint_as_float(v[8 * c + 1]) * inv_l),
+                  pack_bf16x2(__uint_as_float(v[8 * c + 2]) * inv_l, __uint_as_float(v[8 * c + 3]) * inv_l),
+                  pack_bf16x2(__uint_as_float(v[8 * c + 4]) * inv_l, __uint_as_float(v[8 * c + 5]) * inv_l),
+                  pack_bf16x2(__uint_as_float(v[8 * c + 6]) * inv_l, __uint_as_float(v[8 * c + 7]) * inv_l));
+              if (lane < rows_left) dst[c] = val;
+            }
+            return;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(
@@ -1008,11 +1022,19 @@ static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiled
   ap.npairs = (ntiles + 1) / 2;
   ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
   ap.num_items = ap.npairs * L * g.B;
-  const size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
-                       ATTN_RED_FLOATS * 4 + 256;
+  size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
+                 ATTN_RED_FLOATS * 4 + 256;
   const size_t max_smem = 227 * 1024;
   int stages = 4;
   while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
+  if (stages < 2 && ap.nkb <= ATTN_MAX_KB && fixed - ATTN_PATCH_BYTES + ATTN_SLOT_BYTES <= max_smem) {
+    // P of this many columns leaves at most one ring slot: give up the transpose patches (row-per-thread stores) so
+    // that loads and MMAs can overlap at all
+    ap.lean = 1;
+    fixed -= ATTN_PATCH_BYTES;
+    stages = 4;
+    while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
+  }
   if (stages < 1 || ap.nkb > ATTN_MAX_KB) {
     // more columns than the probabilities of a 128-query tile fit in shared memory (n > 576): the consensus of this
     // step runs on CUDA cores in fp32 from the master state (correct for any n that the fp32 engine accepts, far slower)
