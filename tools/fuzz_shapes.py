@@ -12,7 +12,7 @@ for it in range(N):
     dim = int(rng.choice([64, 128, 192, 256, 320, 512]))
     L = int(rng.integers(2, 6))
     p = int(rng.choice([2, 4]))
-    side = int(rng.choice([2, 3, 5, 8, 11, 16, 18]))
+    side = int(rng.choice([2, 3, 5, 8, 11, 16, 18, 22, 24]))
     hh, ww = (side, side) if rng.random() < 0.6 else (int(rng.integers(1, side + 1)), side)
     B = int(rng.integers(1, 5)); T = int(rng.integers(1, 4))
     kw = {}
