@@ -67,7 +67,8 @@ struct GemmCfg {
   static constexpr int THREADS = 32 * (GEMM_CTRL_WARPS + EPI_WARPS);
   static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? (MODE == 0 ? 6 : 5) : 8;   // 32 KB stages + patches must fit 227 KB
+  static constexpr int STAGES = (BN == 256) ? 5 : 8;   // 32 KB stages + patches must fit 227 KB; for K1 five measured
+                                                        // better than four or six (the sixth would fit)
   static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator stages
   static constexpr uint32_t PATCH_BYTES = (MODE == 0) ? 2048 : 4096; // per-warp 32x32 transpose patch (bf16 | f32)
   static_assert(MODE >= 0 && MODE <= 2, "0 = GEMM1+GELU, 1 = GEMM2+combine, 2 = tokeniser");
