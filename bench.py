@@ -315,6 +315,7 @@ def main():
         # host memory and its result back to pinned host memory inside the timed region.  Copies run on two extra
         # streams (one per direction), double-buffered, so step i's D2H and step i+2's H2D overlap step i+1's compute.
         h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)   # one per copy engine / PCIe direction
+        d2h_stream2 = torch.cuda.Stream(dev)           # the 100 MB result goes back as two halves on two DMA queues
         host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
 
         def e2e_loop(nsteps):
@@ -335,13 +336,18 @@ def main():
                 done = torch.cuda.Event()
                 done.record(stream)
                 x.record_stream(stream)
-                with torch.cuda.stream(d2h_stream):            # result back to the host
-                    d2h_stream.wait_event(done)
-                    host_outs[i % 2].copy_(out, non_blocking=True)
-                    out.record_stream(d2h_stream)
+                half = (out.shape[0] + 1) // 2
+                for q, (lo, hi) in ((d2h_stream, (0, half)), (d2h_stream2, (half, out.shape[0]))):
+                    if lo >= hi:
+                        continue
+                    with torch.cuda.stream(q):                 # result back to the host
+                        q.wait_event(done)
+                        host_outs[i % 2][lo:hi].copy_(out[lo:hi], non_blocking=True)
+                        out.record_stream(q)
                 if i + 1 < nsteps:
                     ready = nxt_ready
             stream.wait_stream(d2h_stream)                     # the last D2H is inside the timed region
+            stream.wait_stream(d2h_stream2)
 
         e2e_loop(2)
         barrier()
