@@ -349,7 +349,7 @@ def main():
             stream.wait_stream(d2h_stream)                     # the last D2H is inside the timed region
             stream.wait_stream(d2h_stream2)
 
-        e2e_loop(2)
+        e2e_loop(max(4, args.warmup))                   # allocator and copy queues reach their steady state
         barrier()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ee0.record(stream)
