@@ -335,7 +335,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
             const int kbg_n = 4 * p.d / BK;
             const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
             const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
-            tma_load_2d_2sm(sa, amap, bar, 0, blk * BM);
+            // H streams through once per pair of column tiles: evict-first keeps it from displacing weights / state
+            tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, l2_policy_evict_first());
           } else {
             tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
           }
