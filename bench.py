@@ -9,18 +9,26 @@ configs[1] per GPU (dim=512 L=6 224/14, batch 32, bf16 tensor-core precision), i
 updates of 32x256 columns x 6 levels = 589,824 column-iterations per GPU per step.  N > 1 shards the
 batch (configs[2]: 32 images per GPU, no data-path collective) => weak scaling.
 
+Regime (what the numbers mean): after the W warm-up steps the same forward runs back to back for
+``--preheat-s`` seconds (default 2 s) so that the timed K steps see the SUSTAINED state of the part (1 kW power
+cap, SM clock ~1.4-1.5 GHz), not a sub-second burst at 1.965 GHz.  The SM clock is measured on the device itself
+(``glom_b200_clock_probe``: cycles per %globaltimer nanosecond) immediately before and after the timed region and
+printed next to NVML's (lagging) reading; ``roofline.peak`` is the measured sustained cuBLAS rate when that clock is
+in the sustained band and the burst rate otherwise, and both fractions are printed.
+
 Printed (rank 0, ONE JSON line):
   value      whole-job column-iterations/s with the images already resident in HBM, device-timed
              (CUDA events on the launch stream, barrier + synchronize both sides, MAX over ranks)
   e2e        same metric through the public API with HOST buffers: pinned-host images -> H2D,
              forward, D2H of the returned state into pinned host memory, all inside the timed region
-  roofline   dominant kernel (grouped GEMM1 + GELU, tcgen05): algorithmic FLOPs per launch / its
-             average duration from CUDA events recorded around every launch in the timed region
-  cpu_baseline  the CPU oracle (numpy port of the reference algorithm) on this box's host cores, on a
-             bounded sample of the same workload (rank 0, N = 1 only)
+  roofline   dominant kernel: algorithmic FLOPs per launch / its average duration from CUDA events recorded
+             around every launch in the timed region
+  other_configs  BASELINE configs[3] (per-GPU shape) and configs[4] (3-frame continuation), and a training step
+  cpu_baseline   the reference's own CPU forward on this box's host cores (bounded sample; rank 0, N = 1 only)
 
-``--impl reference`` times that CPU port alone (the reference itself is a Python package that cannot
-travel to the GPU box; the oracle restates it and is pinned against its golden outputs).
+``--impl reference`` times the UNMODIFIED reference package (``$GLOM_REF_PATH`` -> ``baseline/_ref`` ->
+``/root/reference``; torch CPU, all host threads) on the same shapes; if it is not importable on the box it times
+``oracle/glom_oracle_torch.py`` (a torch-CPU restatement pinned on the reference's golden outputs) and says so.
 """
 import argparse
 import json
@@ -34,11 +42,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(dim=512, levels=6, image_size=224, patch_size=14)
+CFG3 = dict(dim=1024, levels=8, image_size=384, patch_size=16)      # BASELINE configs[3], 8 images per GPU, 16 iters
 ITERS = 12
 BATCH_PER_GPU = 32
 N_PATCH = (CFG["image_size"] // CFG["patch_size"]) ** 2
 METRIC = "column-iterations/sec (BxNxLxiters) at dim=512 L=6 224/14"
 UNIT = "column-iterations/s"
+NOMINAL_FLOP_PER_CLK = 148 * 8192.0        # dense bf16: 4096 MAC/clk/SM x 148 SMs (2.25 PFLOP/s at ~1.86 GHz)
 
 
 def flops_per_col_iter(d, L, n):
@@ -56,29 +66,15 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             j = json.load(f)
-        return dict(hbm_gbs=j["hbm_gbs"], tflops=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
-                    tflops_burst=j["bf16_tflops"], source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=j["hbm_gbs"], sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    burst=j["bf16_tflops"], sm_max_mhz=j.get("sm_max_mhz", 1965.0),
+                    sustained_mhz=(j.get("clocks_under_load") or {}).get("sm_mhz_median"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, sustained=1400.0, burst=1590.0, sm_max_mhz=1965.0, sustained_mhz=1300.0,
+                source="fallback (B200_PROFILING.md)")
 
 
-# ------------------------------------------------------------------------------------ CPU port
-def cpu_port_run(batch, iters, reps):
-    """Time the numpy oracle on the host cores.  Returns (col-iters/s, seconds per rep, cores)."""
-    import numpy as np
-    from oracle import glom_oracle as O
-    d, L = CFG["dim"], CFG["levels"]
-    params = O.synth_params(d, L, CFG["image_size"], CFG["patch_size"], seed=0)
-    img = np.random.default_rng(1).standard_normal((batch, 3, CFG["image_size"], CFG["image_size"])).astype(np.float32)
-    O.glom_forward(params, img[:1], patch_size=CFG["patch_size"], iters=1, dtype=np.float32)   # warm BLAS
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.glom_forward(params, img, patch_size=CFG["patch_size"], iters=iters, dtype=np.float32)
-        ts.append(time.perf_counter() - t0)
-    sec = statistics.median(ts)
-    return batch * N_PATCH * L * iters / sec, sec, os.cpu_count()
-
-
+# ------------------------------------------------------------------------------------ CPU arm
 def cpu_model_name():
     try:
         with open("/proc/cpuinfo") as f:
@@ -90,34 +86,181 @@ def cpu_model_name():
     return "unknown"
 
 
+def find_reference():
+    """The unmodified reference package, if importable on this box: (module, where) or (None, why)."""
+    tried = []
+    for cand in (os.environ.get("GLOM_REF_PATH"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if not cand or not os.path.isdir(os.path.join(cand, "glom_pytorch")):
+            continue
+        sys.path.insert(0, cand)
+        try:
+            import importlib
+            mod = importlib.import_module("glom_pytorch")
+            if os.path.realpath(os.path.dirname(mod.__file__)).startswith(os.path.realpath(cand)):
+                return mod, cand
+            tried.append(f"{cand}: shadowed by {mod.__file__}")
+        except Exception as e:      # einops missing, ...
+            tried.append(f"{cand}: {type(e).__name__}: {e}")
+        finally:
+            if sys.path and sys.path[0] == cand:
+                sys.path.pop(0)
+    return None, "; ".join(tried) or "no glom_pytorch package under $GLOM_REF_PATH, baseline/_ref or /root/reference"
+
+
+class CpuArm:
+    """The reference's CPU forward at configs[1] shapes (dim=512 L=6 224/14, fp32, no_grad), all host threads.
+    kind = "reference": the unmodified package's ``Glom.forward``; kind = "port": the torch restatement in oracle/."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        mod, where = find_reference()
+        torch.manual_seed(0)
+        if mod is not None:
+            self.kind, self.where = "reference", where
+            self.model = mod.Glom(**CFG).eval()
+            self.params = None
+        else:
+            from oracle import glom_oracle_torch as OT
+            import glom_pytorch_b200 as G
+            self.kind, self.where = "port", f"oracle/glom_oracle_torch.py ({where})"
+            self.params = {k: v.detach() for k, v in G.Glom(**CFG).state_dict().items()}
+            self.OT = OT
+        self.threads = None
+
+    def forward(self, img, iters):
+        torch = self.torch
+        with torch.no_grad():
+            if self.kind == "reference":
+                return self.model(img, iters=iters)
+            return self.OT.glom_forward(self.params, img, patch_size=CFG["patch_size"], iters=iters)
+
+    def images(self, batch):
+        g = self.torch.Generator().manual_seed(1)
+        return self.torch.randn(batch, 3, CFG["image_size"], CFG["image_size"], generator=g)
+
+    def calibrate(self, budget_s):
+        """Pick the thread count (all logical CPUs or half: SMT rarely helps oneDNN) and the largest batch in
+        {1..32} whose 12-iteration forward is expected to take <= budget_s.  Returns (batch, est seconds)."""
+        torch = self.torch
+        ncpu = os.cpu_count() or 1
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            pass
+        x = self.images(2)
+        best = None
+        for nt in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+            torch.set_num_threads(nt)
+            self.forward(x, 1)                                    # warm the thread pool / oneDNN primitives
+            t0 = time.perf_counter()
+            self.forward(x, 2)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[1]:
+                best = (nt, dt)
+        self.threads = best[0]
+        torch.set_num_threads(self.threads)
+        per_img_iter = best[1] / (2 * 2)
+        batch = 1
+        for b in (2, 4, 8, 16, 32):
+            if per_img_iter * b * ITERS <= budget_s:
+                batch = b
+        return batch, per_img_iter * batch * ITERS
+
+    def time(self, batch, iters, reps, warm=1):
+        x = self.images(batch)
+        for _ in range(warm):
+            self.forward(x, iters)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.forward(x, iters)
+            ts.append(time.perf_counter() - t0)
+        sec = statistics.median(ts)
+        spread = (max(ts) - min(ts)) / sec if len(ts) > 1 else 0.0
+        return batch * N_PATCH * CFG["levels"] * iters / sec, sec, spread
+
+    def describe(self, batch, iters, reps, sec, spread):
+        what = ("unmodified reference glom_pytorch.Glom.forward from " + self.where) if self.kind == "reference" \
+            else ("torch-CPU restatement " + self.where)
+        return (f"{what}; torch {self.torch.__version__} CPU fp32 no_grad, {self.threads} threads; dim=512 L=6 224/14 "
+                f"batch={batch} iters={iters}; median of {reps} reps after warm-up, {sec:.2f} s each, "
+                f"(max-min)/median {spread:.2f}")
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    # each step is a bounded sample of the same shapes, sized so that warmup + K steps end within a few minutes
-    # on any host (the port runs ~5-20 k column-iterations/s): 2 images x 4 iterations = 12,288 column-iterations
-    b, it = 2, 4
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_run(1, 1, 1)
-    v, sec, cores = cpu_port_run(b, it, max(1, args.steps))
+    arm = CpuArm()
+    steps = max(1, args.steps)
+    # a step = one forward of a bounded sample of configs[1]: all 12 iterations, as many of the 32 images as keep
+    # warm-up + K steps within a few minutes on this host
+    batch, _ = arm.calibrate(budget_s=min(6.0, 150.0 / (steps + max(1, args.warmup))))
+    v, sec, spread = arm.time(batch, ITERS, steps, warm=max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1] shapes: dim=512 L=6 224/14; CPU sample batch={b} iters={it} per step",
-                   "batch": b, "iters": it},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
-                         "sample": f"numpy oracle (BLAS + threaded erf on {cores} cores), batch={b} "
-                                   f"iters={it}, median of {max(1, args.steps)} reps, {sec:.2f} s each"},
+        "config": {"workload": f"BASELINE configs[1] shapes: dim=512 L=6 224/14 iters={ITERS}; CPU sample batch={batch} "
+                               f"of 32 per step (the metric is per column-iteration)",
+                   "batch": batch, "iters": ITERS},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "cpu": cpu_model_name(),
+                         "logical_cpus": os.cpu_count(), "sample": arm.describe(batch, ITERS, steps, sec, spread)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ host placement
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and the threads / pinned allocations it creates afterwards) to the CPUs local to its GPU
+    (sysfs local_cpulist of the GPU's PCI function).  Returns a short record for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[local_rank])
+            except (ValueError, IndexError):
+                idx = local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"bound": False, "why": "local cpulist outside the allowed set", "local_cpulist": cpulist}
+        os.sched_setaffinity(0, allowed)
+        node = None
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+        except (OSError, ValueError):
+            pass
+        return {"bound": True, "local_cpulist": cpulist, "numa_node": node, "cpus": len(allowed)}
+    except Exception as e:
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clock, power and throttle reasons DURING the timed region: an NVML polling thread (every
-    ~5 ms); falls back to `nvidia-smi -lms` if pynvml is unavailable."""
+    ~5 ms); falls back to `nvidia-smi -lms` if pynvml is unavailable.  NVML's clock / power readings lag the device by
+    up to a second -- the device-side probe (see device_clock_mhz) is the authoritative clock."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -227,10 +370,12 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--preheat-s", type=float, default=2.0,
+                    help="seconds of back-to-back forwards before the timed region (sustained power / clock state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--train", action="store_true",
-                    help="also time a training step (forward with return_all + backward of a loss on all_levels[7,:,:,-1], "
-                         "README.md:58-90) and add it to the JSON line as \"train\"")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip configs[3] / configs[4] / training extras")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train", action="store_true", help="(kept for compatibility: the training step is timed by default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +386,11 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    try:
+        orig_affinity = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        orig_affinity = None
+    numa = bind_to_gpu_numa(local_rank)       # before torch creates threads / pinned buffers
     import torch
     import torch.distributed as dist
     from glom_pytorch_b200.build import build_library, is_stale
@@ -282,11 +432,29 @@ def main():
         dev_imgs.append(host_imgs[-1].to(dev))
     host_out = torch.empty(B, N_PATCH, L, d, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
+    probe_buf = torch.zeros(8, dtype=torch.int64, device=dev)
 
     def barrier():
         if distributed:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
+
+    def enqueue_clock_probe(slot):
+        _native.clock_probe(probe_buf.data_ptr() + 16 * slot, 150, stream.cuda_stream)
+
+    def preheat(fn, seconds):
+        """Run fn() back to back for `seconds` of device time (checked every 8 calls)."""
+        if seconds <= 0:
+            return 0
+        n = 0
+        t0 = time.perf_counter()
+        while True:
+            for _ in range(8):
+                fn()
+                n += 1
+            torch.cuda.synchronize(dev)
+            if time.perf_counter() - t0 >= seconds:
+                return n
 
     launches = 0
     with torch.no_grad():
@@ -297,22 +465,43 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-            time.sleep(0.3)
+        preheat_steps = preheat(lambda: model(dev_imgs[0], iters=T), args.preheat_s)
         _native.profile_begin()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        if distributed:
+            dist.barrier(device_ids=[local_rank])
+        enqueue_clock_probe(0)
+        torch.cuda.synchronize(dev)
         ev0.record(stream)
         for i in range(args.steps):
             model(dev_imgs[i % NBUF], iters=T)
             launches += model.last_launches
         ev1.record(stream)
+        enqueue_clock_probe(1)
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
         prof = _native.profile_end()
         clocks = sampler.stop() if rank == 0 else None
+        pb = probe_buf.cpu().tolist()
+        dev_mhz = [1e3 * pb[2 * k] / pb[2 * k + 1] if pb[2 * k + 1] else None for k in range(2)]
+
+        # -------- PCIe bandwidth of the buffers the e2e loop moves (attribution of e2e - value)
+        def copy_gbs(dst, src, reps=3):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            c0.record(stream)
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            c1.record(stream)
+            torch.cuda.synchronize(dev)
+            return src.numel() * src.element_size() * reps / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        dev_out_probe = torch.empty(B, N_PATCH, L, d, dtype=torch.float32, device=dev)
+        pcie = {"h2d_gbs": copy_gbs(dev_imgs[0], host_imgs[0]), "d2h_gbs": copy_gbs(host_out, dev_out_probe)}
+        del dev_out_probe
 
         # -------- end to end through the public API with host buffers: every step copies its images from pinned
-        # host memory and its result back to pinned host memory inside the timed region.  Copies run on two extra
+        # host memory and its result back to pinned host memory inside the timed region.  Copies run on extra
         # streams (one per direction), double-buffered, so step i's D2H and step i+2's H2D overlap step i+1's compute.
         h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)   # one per copy engine / PCIe direction
         d2h_stream2 = torch.cuda.Stream(dev)           # the 100 MB result goes back as two halves on two DMA queues
@@ -358,17 +547,68 @@ def main():
         barrier()
         ms_e2e = ee0.elapsed_time(ee1)
 
+    # -------- the other BASELINE configs on this GPU (same sustained state; short: the box is already hot)
+    other = {}
+    peaks = measured_peaks()
+    if not args.no_other_configs and args.precision == "bf16":
+        def timed(fn, reps, warm=3):
+            with torch.no_grad():
+                for _ in range(warm):
+                    fn()
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream)
+                barrier()
+            return a.elapsed_time(b) / reps
+
+        def entry(ms, col_iters, fci, what):
+            tf = fci * col_iters / (ms * 1e-3) / 1e12
+            return {"workload": what, "ms_per_step": ms, "value": col_iters * world / (ms * 1e-3), "unit": UNIT,
+                    "tflops_per_gpu": tf, "frac_sustained": tf / peaks["sustained"], "frac_burst": tf / peaks["burst"]}
+        # configs[4]: 3-frame continuation 12 -> 10 -> 6 with the state carried (README.md:105-111), incl. tokeniser
+        def chain():
+            lv = model(dev_imgs[0], iters=12)
+            lv = model(dev_imgs[1], iters=10, levels=lv)
+            return model(dev_imgs[2], iters=6, levels=lv)
+        ms4 = timed(chain, max(3, args.steps // 8))
+        other["configs[4]"] = entry(ms4, B * N_PATCH * L * 28, flops_per_col_iter(d, L, N_PATCH),
+                                    f"3-frame continuation iters 12->10->6, batch={B}/GPU, three forward calls incl. tokeniser")
+        ms_ra = timed(lambda: model(dev_imgs[0], iters=T, return_all=True), max(3, args.steps // 8))
+        other["configs[1] return_all"] = entry(ms_ra, B * N_PATCH * L * T, flops_per_col_iter(d, L, N_PATCH),
+                                               f"configs[1] with return_all=True ({T + 1} slabs written)")
+        # configs[3]: dim=1024 L=8 384/16 iters=16, 8 images per GPU
+        torch.manual_seed(0)
+        m3 = G.Glom(**CFG3, precision="bf16").to(dev).eval()
+        n3 = (CFG3["image_size"] // CFG3["patch_size"]) ** 2
+        img3 = torch.randn(8, 3, CFG3["image_size"], CFG3["image_size"], generator=torch.Generator().manual_seed(5)).to(dev)
+        ms3 = timed(lambda: m3(img3, iters=16), max(3, args.steps // 8))
+        other["configs[3]"] = entry(ms3, 8 * n3 * CFG3["levels"] * 16, flops_per_col_iter(CFG3["dim"], CFG3["levels"], n3),
+                                    "dim=1024 L=8 384/16 iters=16, batch=8/GPU (the 8-GPU config's per-GPU shard)")
+        del m3, img3
+        torch.cuda.empty_cache()
+
     train = None
-    if args.train:
+    if not args.no_train and not args.no_other_configs and args.precision == "bf16":
+        from glom_pytorch_b200.dp import allreduce_gradients
         model.train()
         tt = 7 if T >= 7 else T
-        for _ in range(2):
+        group = dist.group.WORLD if distributed else None
+
+        def train_step(img):
             model.zero_grad(set_to_none=True)
-            model(dev_imgs[0], iters=T, return_all=True)[tt, :, :, -1].square().mean().backward()
+            loss = model(img, iters=T, return_all=True)[tt, :, :, -1].square().mean()
+            loss.backward()
+            if distributed:
+                allreduce_gradients(model, group)
+        for _ in range(2):
+            train_step(dev_imgs[0])
         barrier()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        nrep = max(3, args.steps // 4)
-        f_ms = b_ms = 0.0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        nrep = max(3, args.steps // 8)
+        f_ms = b_ms = c_ms = 0.0
         for i in range(nrep):
             model.zero_grad(set_to_none=True)
             ev[0].record(stream)
@@ -376,10 +616,18 @@ def main():
             ev[1].record(stream)
             loss.backward()
             ev[2].record(stream)
+            if distributed:
+                allreduce_gradients(model, group)
+            ev[3].record(stream)
             torch.cuda.synchronize(dev)
-            f_ms += ev[0].elapsed_time(ev[1]); b_ms += ev[1].elapsed_time(ev[2])
-        train = {"forward_ms": f_ms / nrep, "backward_ms": b_ms / nrep, "reps": nrep,
-                 "value": B * N_PATCH * L * T / ((f_ms + b_ms) / nrep * 1e-3), "unit": "column-iterations/s per GPU (fwd+bwd)",
+            f_ms += ev[0].elapsed_time(ev[1]); b_ms += ev[1].elapsed_time(ev[2]); c_ms += ev[2].elapsed_time(ev[3])
+        tms = torch.tensor([(f_ms + b_ms + c_ms) / nrep], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        train = {"forward_ms": f_ms / nrep, "backward_ms": b_ms / nrep, "grad_allreduce_ms": c_ms / nrep, "reps": nrep,
+                 "step_ms_max_over_ranks": tms.item(),
+                 "value": global_batch * N_PATCH * L * T / (tms.item() * 1e-3),
+                 "unit": "column-iterations/s (fwd+bwd" + ("+NCCL gradient all-reduce)" if distributed else ")"),
                  "loss": f"mean(all_levels[{tt}, :, :, -1] ** 2)", "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
         model.eval()
 
@@ -387,45 +635,80 @@ def main():
         t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
+        mh = torch.tensor([dev_mhz[0] or 0.0, dev_mhz[1] or 0.0], device=dev, dtype=torch.float64)
+        mh_min = mh.clone()
+        dist.all_reduce(mh_min, op=dist.ReduceOp.MIN)
+        dev_mhz_min = mh_min.tolist()
+    else:
+        dev_mhz_min = dev_mhz
 
     col_iters_step = global_batch * N_PATCH * L * T
     value = col_iters_step * args.steps / (ms_dev * 1e-3)
     e2e_value = col_iters_step * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
-        peaks = measured_peaks()
         rows = B * N_PATCH
         G_ = 2 * L - 1
         kern = {}
         flops = {"gemm1_gelu": 2.0 * rows * 4 * d * d * G_,
                  "gemm2_combine": 2.0 * rows * d * (8 * d * (L - 1) + 4 * d),
                  "attention": 4.0 * N_PATCH * N_PATCH * d * B * L}
+        flops["mlp_fused"] = flops["gemm1_gelu"] + flops["gemm2_combine"]
+        algo_bytes = {"gemm1_gelu": rows * d * 2 * G_ + G_ * 4 * d * d * 2 + rows * G_ * 4 * d * 2,
+                      "gemm2_combine": rows * G_ * 4 * d * 2 + L * d * 8 * d * 2 + rows * L * d * (4 + 2 + 4 + 2 + 2),
+                      # fused MLP kernel: state shadows + tokens in, weights once, fp32 state in/out, C in, shadows out
+                      "mlp_fused": rows * d * 2 * G_ + (G_ * 4 * d * d + L * d * 8 * d) * 2 + rows * L * d * (4 + 2 + 4 + 2 + 2)}
         for k, (ms, cnt) in prof.items():
             if cnt:
                 kern[k] = {"launches": cnt, "avg_us": ms / cnt * 1e3, "ms_per_step": ms / args.steps}
                 if k in flops and args.precision == "bf16":
                     kern[k]["tflops"] = flops[k] / (ms / cnt * 1e-3) / 1e12
-        dom = "gemm1_gelu"
+        cand = [k for k in ("mlp_fused", "gemm1_gelu", "gemm2_combine") if k in kern]
+        dom = max(cand, key=lambda k: kern[k]["ms_per_step"]) if cand else "gemm1_gelu"
+        names = {"mlp_fused": "mlp_kernel (persistent grouped GEMM1+GELU -> GEMM2+combine tiles, tcgen05, H kept in L2)",
+                 "gemm1_gelu": "gemm_kernel<0,256> (grouped GEMM1 + bias + exact-erf GELU, tcgen05)",
+                 "gemm2_combine": "gemm_kernel<1,256> (grouped GEMM2 + 4-way combine, tcgen05)"}
         traffic = None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 traffic = json.load(f)["kernels"][dom]["dram_bytes"] if args.batch_per_gpu == BATCH_PER_GPU else None
         except (OSError, KeyError, ValueError):
             traffic = None
-        roof = {"bound": "tensor", "kernel": "gemm_kernel<0,256> (grouped GEMM1 + bias + exact-erf GELU, tcgen05)",
-                "achieved": kern.get(dom, {}).get("tflops"), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": (kern[dom]["tflops"] / peaks["tflops"]) if kern.get(dom, {}).get("tflops") else None,
+        # regime: the device-side clock decides which measured peak is the denominator
+        mhz = [m for m in dev_mhz_min if m]
+        clk = sum(mhz) / len(mhz) if mhz else None
+        band = 0.85 * peaks["sm_max_mhz"]
+        regime = "unknown" if clk is None else ("sustained" if clk < band else "burst")
+        peak = peaks["burst"] if regime == "burst" else peaks["sustained"]
+        ach = kern.get(dom, {}).get("tflops")
+        whole_tf = flops_per_col_iter(d, L, N_PATCH) * col_iters_step / world / (ms_dev / args.steps * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": names.get(dom, dom), "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": (ach / peak) if ach else None,
+                "frac_of_sustained_peak": (ach / peaks["sustained"]) if ach else None,
+                "frac_of_burst_peak": (ach / peaks["burst"]) if ach else None,
+                "frac_of_clock_scaled_nominal": (ach * 1e12 / (NOMINAL_FLOP_PER_CLK * clk * 1e6)) if (ach and clk) else None,
+                "regime": regime,
+                "regime_rule": f"device SM clock {clk:.0f} MHz {'<' if regime == 'sustained' else '>='} 0.85 x {peaks['sm_max_mhz']:.0f} "
+                               f"-> peak = bf16_tflops{'_sustained' if regime != 'burst' else ''}" if clk else "no device clock",
+                "peaks": {"sustained": peaks["sustained"], "burst": peaks["burst"], "hbm_gbs": peaks["hbm_gbs"],
+                          "sustained_measured_at_mhz": peaks["sustained_mhz"], "source": peaks["source"]},
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read+write)",
-                "algorithmic_bytes": rows * d * 2 * G_ + G_ * 4 * d * d * 2 + rows * G_ * 4 * d * 2,
-                "peak_source": peaks["source"],
-                "flops_per_launch": flops[dom],
-                "whole_step": {"tflops": flops_per_col_iter(d, L, N_PATCH) * col_iters_step / world /
-                               (ms_dev / args.steps * 1e-3) / 1e12,
+                "algorithmic_bytes": algo_bytes.get(dom),
+                "flops_per_launch": flops.get(dom),
+                "whole_step": {"tflops": whole_tf,
                                "hbm_gbs_algorithmic": bytes_per_iter(d, L, N_PATCH, B) * T /
-                               (ms_dev / args.steps * 1e-3) / 1e9},
+                               (ms_dev / args.steps * 1e-3) / 1e9,
+                               "frac_tensor": whole_tf / peak, "frac_of_sustained_peak": whole_tf / peaks["sustained"],
+                               "frac_of_burst_peak": whole_tf / peaks["burst"]},
                 "kernels": kern}
-        roof["whole_step"]["frac_tensor"] = roof["whole_step"]["tflops"] / peaks["tflops"]
         roof["whole_step"]["frac_hbm"] = roof["whole_step"]["hbm_gbs_algorithmic"] / peaks["hbm_gbs"]
+        if clocks is not None:
+            clocks["device_sm_mhz_before"] = dev_mhz_min[0]
+            clocks["device_sm_mhz_after"] = dev_mhz_min[1]
+            clocks["device_how"] = ("glom_b200_clock_probe: clock64 cycles per %globaltimer ns over 150 us, one thread, "
+                                    "enqueued right before / after the timed region (min over ranks)")
+            clocks["preheat_s"] = args.preheat_s
+            clocks["preheat_steps"] = preheat_steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -435,22 +718,36 @@ def main():
             "config": {"workload": f"BASELINE configs[{1 if world == 1 else 2}]: dim=512 L=6 224/14 iters={T} "
                                    f"batch={B}/GPU (global {global_batch}), Glom.forward incl. tokeniser",
                        "global_batch": global_batch, "iters": T, "parallelism": f"dp{world} (batch shards, no collective)",
-                       "l2": "per-step working set ~1.1 GB (H 369 MB, state 100 MB fp32 + shadows, weights 46 MB) "
+                       "regime": f"{args.preheat_s:g} s of back-to-back forwards before the timed region (sustained power state)",
+                       "l2": "per-step working set ~1 GB (state 100 MB fp32 + shadows, H 369 MB, weights 46 MB) "
                              "> 126 MB L2; input images rotate over 4 buffers; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_imgs[0].numel() * 4 * world,
-                    "d2h_bytes_per_step": host_out.numel() * 4 * world},
+                    "d2h_bytes_per_step": host_out.numel() * 4 * world,
+                    "pcie": pcie, "host_numa": numa},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
         }
+        if other:
+            line["other_configs"] = other
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores = cpu_port_run(4, 3, 5)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
-                                    "sample": f"numpy oracle, same shapes, batch=4 iters=3, median of 5 reps "
-                                              f"({sec:.2f} s each); BLAS + threaded erf on {cores} cores"}
+            # the reference arm's own code path, in a child process with the ORIGINAL CPU affinity (this process and
+            # its thread pools are pinned to the GPU's NUMA node), on a bounded sample: 3 timed forwards
+            def unbind():
+                if orig_affinity:
+                    os.sched_setaffinity(0, orig_affinity)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                                    "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                   timeout=600, preexec_fn=unbind)
+                ref_line = json.loads(r.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref_line["cpu_baseline"]
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
+                                        "sample": f"CPU arm failed: {type(ex).__name__}: {ex}"}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier(device_ids=[local_rank])

@@ -16,6 +16,7 @@ EXPORTS = (
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
     "glom_b200_backward", "glom_b200_backward_workspace_bytes",
+    "glom_b200_clock_probe",
 )
 PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize")
 
@@ -75,6 +76,8 @@ def load():
     lib.glom_b200_backward.argtypes = [ctypes.POINTER(Cfg), ctypes.POINTER(WeightsRef), vp, vp, vp, vp,
                                        ctypes.POINTER(Grads), i32, i32, i32, vp, sz, vp]
     lib.glom_b200_backward.restype = i32
+    lib.glom_b200_clock_probe.argtypes = [vp, i32, vp]
+    lib.glom_b200_clock_probe.restype = i32
     for f in ("glom_b200_packed_weight_bytes", "glom_b200_pack_weights", "glom_b200_workspace_bytes",
               "glom_b200_workspace_offset", "glom_b200_forward", "glom_b200_tokenize"):
         getattr(lib, f).restype = i32
@@ -168,3 +171,8 @@ def backward(cfg, weight_ptrs, tokens_ptr, pos_ptr, states_ptr, grad_out_ptr, gr
     check(load().glom_b200_backward(ctypes.byref(cfg), ctypes.byref(w), tokens_ptr, pos_ptr, states_ptr,
                                     grad_out_ptr, ctypes.byref(g), batch, iters, int(grad_all), ws_ptr, ws_bytes,
                                     stream))
+
+
+def clock_probe(out_ptr, spin_us, stream):
+    """Enqueue the SM clock probe: out_ptr -> 2 x uint64 device words {cycles, ns} (read after a synchronize)."""
+    check(load().glom_b200_clock_probe(out_ptr, spin_us, stream))

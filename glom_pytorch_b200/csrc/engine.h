@@ -113,6 +113,8 @@ cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const f
 cudaError_t launch_tokenize(const float* img, const float* w, const float* bias, float* tokens, int B, int H, int W,
                             int p, int d, cudaStream_t st, int* launches, Profiler* prof);
 
+cudaError_t launch_clock_probe(unsigned long long* out, unsigned long long spin_ns, cudaStream_t st);
+
 // bf16 tokeniser: patchify + cast (CUDA cores), then the tcgen05 GEMM
 cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16* patches, __nv_bfloat16* wtok, int B,
                                  int H, int W, int p, int d, int kp, cudaStream_t st, int* launches);

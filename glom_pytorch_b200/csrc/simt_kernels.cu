@@ -472,4 +472,24 @@ cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- SM clock probe (bench.py's regime record)
+// One thread spins for `spin_ns` of %globaltimer and reports the SM cycles that elapsed: cycles / ns is the SM clock
+// the device actually ran at (NVML's clock reading lags by up to a second and misses short power-cap excursions).
+__global__ void clock_probe_kernel(unsigned long long* out, unsigned long long spin_ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < spin_ns);
+  const long long c1 = clock64();
+  out[0] = (unsigned long long)(c1 - c0);
+  out[1] = t1 - t0;
+}
+cudaError_t launch_clock_probe(unsigned long long* out, unsigned long long spin_ns, cudaStream_t st) {
+  clock_probe_kernel<<<1, 1, 0, st>>>(out, spin_ns);
+  return cudaGetLastError();
+}
+
+
 }  // namespace glom

@@ -12,8 +12,16 @@ Mirrors the reference's public surface (glom_pytorch/glom_pytorch.py):
 What differs: the loop body (:131-145) plus GroupedFeedForward.forward / ConsensusAttention.forward is
 one call into ``libglom_b200.so`` (C ABI in include/glom_b200.h).  CUDA sm_100 only; there is no CPU / eager
 fallback -- inputs on other devices raise.  Under autograd the loop is a ``torch.autograd.Function`` whose backward
-is the engine's fp32 CUDA kernel set (``glom_b200_backward``): the forward keeps S_0..S_T and the reverse pass
-recomputes each step's intermediates (README.md:58-90 training use).
+is ``glom_b200_backward`` (bf16 engine: the MLP and consensus GEMMs of the reverse pass on tcgen05 tensor cores, the
+softmax / normalisation / bias reductions in fp32 on CUDA cores; fp32 engine: everything fp32 on CUDA cores): the
+forward keeps S_0..S_T and the reverse pass recomputes each step's intermediates (README.md:58-90 training use).
+The backward is once-differentiable and accumulates with ``red.add`` atomics, so gradients are reproducible only up
+to fp32 summation order.
+
+Packed weights: the MLP weights are repacked (one small kernel) on EVERY call while ``self.training``; in eval mode
+the packed copy is cached and keyed on each parameter's ``(data_ptr, _version)`` and dropped by ``load_state_dict``,
+``.to()`` / ``.cuda()`` / ``.half()``-style ``_apply`` calls and ``invalidate_packed()``.  In-place edits through
+``param.data`` do not bump ``_version``: call ``invalidate_packed()`` after them in eval mode.
 
 Engine-only knob (keyword-only, additive): ``precision`` = ``"bf16"`` (default; tcgen05 tensor cores,
 bf16 operands, fp32 accumulate and fp32 state -- the arithmetic of the reference under
@@ -99,7 +107,7 @@ class ConsensusAttention(nn.Module):
             raise RuntimeError(f"local_consensus_radius needs n == num_patches ({side * side}), got {n} "
                                "(the reference's masked_fill_ fails the same way)")
         key = getattr(self, "_mask_key", None)
-        if key is None or key[0] is not self.non_local_mask:
+        if key is None or key[0] is not self.non_local_mask or key[2] != self.non_local_mask._version:
             ar = torch.arange(side, device=mask.device)
             hh, ww = torch.meshgrid(ar, ar, indexing="ij")
             co = torch.stack((hh.reshape(-1), ww.reshape(-1)), -1)
@@ -108,13 +116,23 @@ class ConsensusAttention(nn.Module):
             d2_max = int(kept.max().item()) if kept.numel() else -1
             if not torch.equal(d2 > d2_max, mask):
                 raise RuntimeError("attention.non_local_mask is not a radius mask on the patch grid")
-            self._mask_key = (self.non_local_mask, d2_max)
+            self._mask_key = (self.non_local_mask, d2_max, self.non_local_mask._version)
         return side, self._mask_key[1]
+
+    def _load_from_state_dict(self, *args, **kwargs):     # a loaded mask (copied in place) is re-derived
+        self._mask_key = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def __getstate__(self):
+        st = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        st = dict(st)
+        st.pop("_mask_key", None)
+        return st
 
 
 class _ColumnUpdate(torch.autograd.Function):
     """The loop glom_pytorch.py:131-145 as one differentiable op: forward = glom_b200_forward (all states kept),
-    backward = glom_b200_backward (fp32, recompute per step)."""
+    backward = glom_b200_backward (recompute per step; tensor-core GEMMs for the bf16 engine)."""
 
     @staticmethod
     def forward(ctx, module, iters, return_all, tokens, pos, state0, init_levels, *weights):
@@ -122,10 +140,12 @@ class _ColumnUpdate(torch.autograd.Function):
         states = module._run_engine(tokens, pos, state0, init_levels, iters, True)      # (T+1, B, n, L, d)
         ctx.module, ctx.iters, ctx.return_all = module, iters, return_all
         ctx.had_state0 = state0 is not None
+        ctx.want_state0 = state0 is not None and state0.requires_grad
         ctx.save_for_backward(tokens, pos, states, *weights)
         return states if return_all else states[iters]
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         module, iters = ctx.module, ctx.iters
         tokens, pos, states, *weights = ctx.saved_tensors
@@ -148,7 +168,8 @@ class _ColumnUpdate(torch.autograd.Function):
                              grad_out.data_ptr(), {k: (None if v is None else v.data_ptr()) for k, v in g.items()},
                              b, iters, ctx.return_all, ws.data_ptr(), ws.numel(),
                              torch.cuda.current_stream(device).cuda_stream)
-        return (None, None, None, g["d_tokens"], g["d_pos"], g["d_state0"], g["d_init"], *[g[k] for k in names])
+        return (None, None, None, g["d_tokens"], g["d_pos"], g["d_state0"] if ctx.want_state0 else None, g["d_init"],
+                *[g[k] for k in names])
 
 
 def zeros_like32(t):
@@ -177,9 +198,50 @@ class Glom(nn.Module):
         self.attention = ConsensusAttention(num_patches_side, attend_self=consensus_self,
                                             local_consensus_radius=local_consensus_radius)
         self._packed = None          # (key, tensor)
-        self._workspace = None       # grown on demand, reused across calls (video continuation)
+        self._scratch = {}           # (slot, device index, stream) -> buffer, grown on demand, reused across calls
         self.use_native_tokenizer = True
         self.last_launches = 0
+
+    # ------------------------------------------------------------------ cache hygiene
+    _SCRATCH_ATTRS = ("_packed", "_scratch", "_tok_launches")
+
+    def invalidate_packed(self):
+        """Drop the cached packed copy of the MLP weights (needed after in-place ``param.data`` edits in eval mode)."""
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):                 # .to() / .cuda() / .float() ...: parameters are replaced
+        self._packed = None
+        self._scratch = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):      # load_state_dict copies in place: versions bump, but be explicit
+        self._packed = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def __getstate__(self):                                # torch.save(model) / pickle: no scratch buffers
+        st = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)
+        st["_packed"], st["_scratch"] = None, {}
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_packed":
+                new.__dict__[k] = None
+            elif k == "_scratch":
+                new.__dict__[k] = {}
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    @property
+    def _workspace(self):
+        """The forward workspace of the current device / stream (diagnostics and tests)."""
+        dev = torch.cuda.current_device()
+        return self._scratch.get(("_workspace", dev, torch.cuda.current_stream(dev).cuda_stream))
 
     # ------------------------------------------------------------------ engine plumbing
     def _mlp_params(self):
@@ -190,8 +252,10 @@ class Glom(nn.Module):
 
     def _packed_weights(self, cfg, device, stream):
         params = self._mlp_params()
-        key = (self.precision, device, tuple((p.data_ptr(), p._version) for p in params))
-        if self._packed is not None and self._packed[0] == key:
+        key = (self.precision, (device, stream), tuple((p.data_ptr(), p._version) for p in params))
+        # training: parameters change between calls in ways the key cannot always see (optimisers that write through
+        # .data, EMA updates): repack every call (one ~30 us kernel).  eval: cached on (data_ptr, _version).
+        if not self.training and self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         srcs = []
         for p in params:
@@ -200,16 +264,24 @@ class Glom(nn.Module):
                 t = t.float().contiguous()
             srcs.append(t)
         nbytes = _native.packed_weight_bytes(cfg)
-        packed = _aligned_bytes(nbytes, device)
+        if self._packed is not None and self._packed[1].device == device and self._packed[1].numel() == nbytes \
+                and self._packed[0][:2] == key[:2]:
+            packed = self._packed[1]            # same stream order as the kernels that read it: safe to overwrite
+        else:
+            packed = _aligned_bytes(nbytes, device)
         _native.pack_weights(cfg, [t.data_ptr() for t in srcs], packed.data_ptr(), nbytes, stream)
         self._packed = (key, packed)
         return packed
 
     def _get_workspace(self, nbytes, device, slot="_workspace"):
-        ws = getattr(self, slot, None)
-        if ws is None or ws.device != device or ws.numel() < nbytes:
+        """Scratch buffer per (purpose, device, stream): two forwards of one module on different streams never share
+        H / C / shadow buffers, and a buffer is only ever reused by work enqueued on the stream that last used it."""
+        key = (slot, device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
+        ws = self._scratch.get(key)
+        if ws is None or ws.numel() < nbytes:
             ws = _aligned_bytes(nbytes, device)
-            setattr(self, slot, ws)
+            self._scratch[key] = ws
         return ws
 
     def engine_cfg(self, n, precision=None):

@@ -162,6 +162,11 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
 GLOM_B200_API int glom_b200_profile_begin(void);
 GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kind, int kinds);
 
+/* Measurement aid (bench.py): one device thread spins for `spin_us` microseconds of %globaltimer and writes
+ * {SM cycles elapsed, nanoseconds elapsed} to out_cycles_ns[0..1] (device memory, 16 bytes): cycles / ns is the SM
+ * clock in GHz the device actually ran at when the probe executed.  Enqueued on `stream`; the caller synchronises. */
+GLOM_B200_API int glom_b200_clock_probe(uint64_t* out_cycles_ns, int spin_us, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -303,6 +303,108 @@ def test_config2_dims_against_cpu_oracle():
     check_bf16(out, ref, "config2-dims")
 
 
+def _oracle_params(m):
+    return {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+
+def test_config2_dims_all_12_iterations_against_cpu_oracle():
+    """BASELINE configs[1] dims and iteration count (d=512 L=6 N=256, iters=12), B=2, return_all: every one of the 12
+    time steps of the bf16 engine against the fp32 CPU oracle (existing bf16 tolerance per step)."""
+    m = full_model("bf16")
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        out = m(img.to(DEV), iters=12, return_all=True).cpu().numpy()
+    ref = O.glom_forward(_oracle_params(m), img.numpy(), patch_size=14, iters=12, return_all=True, dtype=np.float32)
+    assert out.shape == ref.shape == (13, 2, 256, 6, 512)
+    check_bf16(out, ref, "config2-dims x 12 iterations")
+
+
+def test_config5_chain_12_10_6_against_cpu_oracle():
+    """BASELINE configs[4] (README.md:105-111): three frames, iters 12 -> 10 -> 6 with the state carried, d=512 L=6
+    N=256, B=2: 28 chained iterations.  The engine carries ITS OWN state between the calls, the oracle its own; every
+    time step of every call is compared (drift over the whole chain stays inside the per-step bf16 tolerance)."""
+    m = full_model("bf16")
+    P = _oracle_params(m)
+    g = torch.Generator().manual_seed(12)
+    lv_e, lv_o = None, None
+    for f, T in enumerate((12, 10, 6)):
+        img = torch.randn(2, 3, 224, 224, generator=g)
+        with torch.no_grad():
+            all_e = m(img.to(DEV), iters=T, levels=lv_e, return_all=True)
+        all_o = O.glom_forward(P, img.numpy(), patch_size=14, iters=T, levels=lv_o, return_all=True, dtype=np.float32)
+        check_bf16(all_e.cpu().numpy(), all_o, f"chain frame {f} ({T} iterations)")
+        lv_e, lv_o = all_e[-1].clone(), all_o[-1]
+
+
+def test_config4_dims_against_cpu_oracle():
+    """BASELINE configs[3] dims (d=1024 L=8 384/16 -> N=576, the lean consensus variant), B=1, 3 iterations, against the
+    fp32 CPU oracle (not the engine's own fp32 path)."""
+    torch.manual_seed(0)
+    kw = dict(dim=1024, levels=8, image_size=384, patch_size=16)
+    m = G.Glom(**kw, precision="bf16").to(DEV).eval()
+    img = torch.randn(1, 3, 384, 384, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        out = m(img.to(DEV), iters=3, return_all=True).cpu().numpy()
+    ref = O.glom_forward(_oracle_params(m), img.numpy(), patch_size=16, iters=3, return_all=True, dtype=np.float32)
+    check_bf16(out, ref, "config4-dims vs oracle")
+
+
+def test_radius_mask_and_consensus_self_at_config2_dims():
+    """local_consensus_radius = 2.5 together with consensus_self=True at N=256 / d=512 (16 x 16 patch grid), B=1, 3
+    iterations, bf16 and fp32 engines against the CPU oracle."""
+    torch.manual_seed(3)
+    m = G.Glom(**FULL, precision="bf16", consensus_self=True, local_consensus_radius=2.5).to(DEV).eval()
+    m32 = G.Glom(**FULL, precision="fp32", consensus_self=True, local_consensus_radius=2.5).to(DEV).eval()
+    m32.load_state_dict(m.state_dict())
+    img = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(13))
+    with torch.no_grad():
+        out = m(img.to(DEV), iters=3, return_all=True).cpu().numpy()
+        out32 = m32(img.to(DEV), iters=3, return_all=True).cpu().numpy()
+    ref = O.glom_forward(_oracle_params(m), img.numpy(), patch_size=14, iters=3, return_all=True, dtype=np.float32,
+                         consensus_self=True, local_consensus_radius=2.5)
+    assert np.abs(out32 - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+    check_bf16(out, ref, "radius 2.5 + consensus_self at N=256")
+    # and the default (masked-diagonal) attention with a radius
+    m2 = G.Glom(**FULL, precision="bf16", local_consensus_radius=1.5).to(DEV).eval()
+    with torch.no_grad():
+        out2 = m2(img.to(DEV), iters=2, return_all=True).cpu().numpy()
+    ref2 = O.glom_forward(_oracle_params(m2), img.numpy(), patch_size=14, iters=2, return_all=True, dtype=np.float32,
+                          local_consensus_radius=1.5)
+    check_bf16(out2, ref2, "radius 1.5 at N=256")
+
+
+def test_packed_weight_cache_follows_the_parameters():
+    """in-place edits through .data do not bump _version.  train(): repacked every call; eval(): cached,
+    dropped by load_state_dict / invalidate_packed()."""
+    torch.manual_seed(5)
+    m = G.Glom(dim=128, levels=3, image_size=32, patch_size=4).to(DEV)
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    with torch.no_grad():
+        m.eval()
+        a = m(x, iters=2)
+        m.bottom_up.net[1].weight.data.mul_(0.5)
+        assert torch.equal(m(x, iters=2), a)                # documented: stale until invalidated
+        m.invalidate_packed()
+        b = m(x, iters=2)
+        assert not torch.equal(a, b)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd["bottom_up.net.1.weight"].mul_(2.0)
+        m.load_state_dict(sd)                               # back to the original weights
+        assert torch.allclose(m(x, iters=2), a, rtol=0, atol=1e-6)
+        m.train()
+        c = m(x, iters=2)
+        m.top_down.net[3].weight.data.mul_(0.25)
+        assert not torch.equal(m(x, iters=2), c)            # training mode sees .data edits immediately
+
+
+def test_clock_probe_reports_a_plausible_sm_clock():
+    buf = torch.zeros(2, dtype=torch.int64, device=DEV)
+    _native.clock_probe(buf.data_ptr(), 200, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    cyc, ns = buf.tolist()
+    assert ns >= 200_000 and 500 <= 1e3 * cyc / ns <= 2200, (cyc, ns)
+
+
 def test_config2_full_size_properties():
     """Size-independent properties at BASELINE configs[1] (B=32, iters=12):
     (1) continuation additivity 12 == 6 + 6 bit-exactly (README.md:105-111);

@@ -86,3 +86,28 @@ def test_radius_mask_matches_reference_semantics():
     assert m.shape == (16, 16) and not m.diagonal().any()
     # (0,0) -> (1,1) is sqrt2 <= 1.5 (kept); (0,0) -> (0,2) is 2 > 1.5 (masked)
     assert not m[0, 5] and m[0, 2]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_torch_cpu_restatement_matches_reference_golden(name):
+    """oracle/glom_oracle_torch.py (bench.py's multi-threaded CPU arm when the reference package is not importable)
+    against the same golden outputs of the live reference; fp32 arithmetic: <= 1e-4 * scale."""
+    import torch
+    from oracle import glom_oracle_torch as OT
+    case, params, outs = load(name)
+    kw = dict(patch_size=case["patch_size"], consensus_self=case.get("consensus_self", False),
+              local_consensus_radius=case.get("local_consensus_radius", 0))
+    if case.get("frames"):
+        levels = None
+        for f in range(case["frames"]):
+            img, _ = inputs(case, f)
+            levels = OT.glom_forward(params, img, iters=case["iters"][f], levels=levels, **kw)
+            ref = outs[f"out{f}"]
+            assert np.abs(levels.numpy() - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
+    else:
+        img, lv = inputs(case)
+        got = OT.glom_forward(params, img, iters=case["iters"], levels=lv, return_all=case.get("return_all", False),
+                              **kw).numpy()
+        ref = outs["out0"]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max()))
