@@ -466,7 +466,6 @@ def main():
         if rank == 0:
             sampler.start()
         preheat_steps = preheat(lambda: model(dev_imgs[0], iters=T), args.preheat_s)
-        _native.profile_begin()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if distributed:
             dist.barrier(device_ids=[local_rank])
@@ -480,10 +479,22 @@ def main():
         enqueue_clock_probe(1)
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
+        # -------- the same K steps again, back to back, with CUDA events around EVERY kernel launch (library hook):
+        # per-kernel durations for the roofline.  Kept out of the region above because an event between two kernels
+        # disables their programmatic (PDL) overlap and costs ~1 us each: the instrumented pass is a few % slower.
+        _native.profile_begin()
+        ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ep0.record(stream)
+        for i in range(args.steps):
+            model(dev_imgs[i % NBUF], iters=T)
+        ep1.record(stream)
+        enqueue_clock_probe(2)
+        barrier()
+        ms_prof = ep0.elapsed_time(ep1)
         prof = _native.profile_end()
         clocks = sampler.stop() if rank == 0 else None
         pb = probe_buf.cpu().tolist()
-        dev_mhz = [1e3 * pb[2 * k] / pb[2 * k + 1] if pb[2 * k + 1] else None for k in range(2)]
+        dev_mhz = [1e3 * pb[2 * k] / pb[2 * k + 1] if pb[2 * k + 1] else None for k in range(3)]
 
         # -------- PCIe bandwidth of the buffers the e2e loop moves (attribution of e2e - value)
         def copy_gbs(dst, src, reps=3):
@@ -635,7 +646,7 @@ def main():
         t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
-        mh = torch.tensor([dev_mhz[0] or 0.0, dev_mhz[1] or 0.0], device=dev, dtype=torch.float64)
+        mh = torch.tensor([m or 0.0 for m in dev_mhz], device=dev, dtype=torch.float64)
         mh_min = mh.clone()
         dist.all_reduce(mh_min, op=dist.ReduceOp.MIN)
         dev_mhz_min = mh_min.tolist()
@@ -675,7 +686,7 @@ def main():
         except (OSError, KeyError, ValueError):
             traffic = None
         # regime: the device-side clock decides which measured peak is the denominator
-        mhz = [m for m in dev_mhz_min if m]
+        mhz = [m for m in dev_mhz_min[:2] if m]
         clk = sum(mhz) / len(mhz) if mhz else None
         band = 0.85 * peaks["sm_max_mhz"]
         regime = "unknown" if clk is None else ("sustained" if clk < band else "burst")
@@ -700,11 +711,15 @@ def main():
                                (ms_dev / args.steps * 1e-3) / 1e9,
                                "frac_tensor": whole_tf / peak, "frac_of_sustained_peak": whole_tf / peaks["sustained"],
                                "frac_of_burst_peak": whole_tf / peaks["burst"]},
+                "instrumented_ms_per_step": ms_prof / args.steps,
+                "how": "per-kernel CUDA events (library hook) over a second pass of the same K steps right after the timed "
+                       "region, same sustained state; `value` / `ms_per_step` come from the un-instrumented pass",
                 "kernels": kern}
         roof["whole_step"]["frac_hbm"] = roof["whole_step"]["hbm_gbs_algorithmic"] / peaks["hbm_gbs"]
         if clocks is not None:
             clocks["device_sm_mhz_before"] = dev_mhz_min[0]
             clocks["device_sm_mhz_after"] = dev_mhz_min[1]
+            clocks["device_sm_mhz_after_instrumented_pass"] = dev_mhz_min[2]
             clocks["device_how"] = ("glom_b200_clock_probe: clock64 cycles per %globaltimer ns over 150 us, one thread, "
                                     "enqueued right before / after the timed region (min over ranks)")
             clocks["preheat_s"] = args.preheat_s

@@ -16,9 +16,9 @@ EXPORTS = (
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
     "glom_b200_backward", "glom_b200_backward_workspace_bytes",
-    "glom_b200_clock_probe",
+    "glom_b200_clock_probe", "glom_b200_mlp_schedule", "glom_b200_islands",
 )
-PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize")
+PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize", "mlp_fused")
 
 
 class Cfg(ctypes.Structure):
@@ -76,6 +76,10 @@ def load():
     lib.glom_b200_backward.argtypes = [ctypes.POINTER(Cfg), ctypes.POINTER(WeightsRef), vp, vp, vp, vp,
                                        ctypes.POINTER(Grads), i32, i32, i32, vp, sz, vp]
     lib.glom_b200_backward.restype = i32
+    lib.glom_b200_mlp_schedule.argtypes = [ctypes.POINTER(Cfg), i32, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    lib.glom_b200_mlp_schedule.restype = i32
+    lib.glom_b200_islands.argtypes = [vp, i32, i32, i32, i32, i32, ctypes.c_float, vp, vp, vp, vp, vp, vp]
+    lib.glom_b200_islands.restype = i32
     lib.glom_b200_clock_probe.argtypes = [vp, i32, vp]
     lib.glom_b200_clock_probe.restype = i32
     for f in ("glom_b200_packed_weight_bytes", "glom_b200_pack_weights", "glom_b200_workspace_bytes",
@@ -176,3 +180,18 @@ def backward(cfg, weight_ptrs, tokens_ptr, pos_ptr, states_ptr, grad_out_ptr, gr
 def clock_probe(out_ptr, spin_us, stream):
     """Enqueue the SM clock probe: out_ptr -> 2 x uint64 device words {cycles, ns} (read after a synchronize)."""
     check(load().glom_b200_clock_probe(out_ptr, spin_us, stream))
+
+
+def mlp_schedule(cfg, batch, num_sms=148):
+    """Work list of the merged MLP kernel: (list of (kind, z, m_blk, n_blk), delay).  Host only."""
+    n, dl = ctypes.c_int(), ctypes.c_int()
+    check(load().glom_b200_mlp_schedule(ctypes.byref(cfg), batch, num_sms, None, 0, ctypes.byref(n), ctypes.byref(dl)))
+    buf = (ctypes.c_int32 * (4 * n.value))()
+    check(load().glom_b200_mlp_schedule(ctypes.byref(cfg), batch, num_sms, buf, n.value, ctypes.byref(n), ctypes.byref(dl)))
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n.value)], dl.value
+
+
+def islands(states_ptr, slabs, side_h, side_w, levels, dim, threshold, cos_right_ptr, cos_down_ptr, agreement_ptr,
+            labels_ptr, num_islands_ptr, stream):
+    check(load().glom_b200_islands(states_ptr, slabs, side_h, side_w, levels, dim, threshold, cos_right_ptr, cos_down_ptr,
+                                   agreement_ptr, labels_ptr, num_islands_ptr, stream))

@@ -12,7 +12,7 @@ namespace glom {
 
 // Optional per-kernel CUDA-event timing (bench.py's roofline numbers).  Events are recorded on the
 // launch stream around each kernel; nothing is synchronised until the caller reads them.
-enum ProfKind { PROF_ATTN = 0, PROF_GEMM1 = 1, PROF_GEMM2 = 2, PROF_PREP = 3, PROF_TOKENIZE = 4, PROF_KINDS = 5 };
+enum ProfKind { PROF_ATTN = 0, PROF_GEMM1 = 1, PROF_GEMM2 = 2, PROF_PREP = 3, PROF_TOKENIZE = 4, PROF_MLP = 5, PROF_KINDS = 6 };
 struct Profiler {
   bool enabled = false;
   std::vector<cudaEvent_t> ev;
@@ -65,6 +65,8 @@ struct WorkspaceLayout {
   size_t c_bytes;
   size_t nsq_off[2];   // squared-norm partials              (rows, L, nparts) f32
   size_t nsq_bytes;
+  size_t sched_off;    // bf16 engine, merged MLP kernel: per iteration a tile counter + ready[L * row blocks] (ints)
+  size_t sched_bytes;
   size_t total;
 };
 WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, int return_all);
@@ -90,9 +92,16 @@ cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* i
                         const float* tokens, float* s32_dst, __nv_bfloat16* sb, __nv_bfloat16* sp,
                         __nv_bfloat16* xb, float* nsq, cudaStream_t st, int* launches, Profiler* prof);
 
-// one Jacobi step on tensor cores: consensus -> C ; GEMM1+GELU -> H ; GEMM2+combine -> state t+1
-int step_bf16(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st,
+// one Jacobi step on tensor cores.  sched == nullptr (or dim % 256 != 0): GEMM1+GELU -> H ; consensus -> C ;
+// GEMM2+combine -> state t+1 (three launches).  Otherwise: consensus -> C, then the merged persistent MLP kernel
+// (mlp_kernel.cu; `sched` = this step's zeroed scheduler / dependency counters, mlp_sched_ints(g) ints).
+int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn enc, int num_sms, cudaStream_t st,
               int* launches, char* err, size_t errlen, Profiler* prof);
+bool mlp_fused_supported(const Geometry& g);
+size_t mlp_sched_ints(const Geometry& g);
+int mlp_schedule_dump(const Geometry& g, int num_sms, int* out, int capacity, int* num_tiles, int* delay);
+int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn enc, int num_sms,
+                        cudaStream_t st, int* launches, char* err, size_t errlen, Profiler* prof);
 
 struct F32Buffers {
   const float* s_in;  float* s_out;
@@ -112,6 +121,11 @@ cudaError_t launch_pack(int d, int L, int precision, const float* bu_w1, const f
 
 cudaError_t launch_tokenize(const float* img, const float* w, const float* bias, float* tokens, int B, int H, int W,
                             int p, int d, cudaStream_t st, int* launches, Profiler* prof);
+
+// island analytics on state slabs (islands.cu)
+cudaError_t launch_islands(const float* states, int slabs, int side_h, int side_w, int L, int d, float threshold,
+                           float* cos_right, float* cos_down, float* agreement, int* labels, int* num_islands,
+                           cudaStream_t st, int* launches);
 
 cudaError_t launch_clock_probe(unsigned long long* out, unsigned long long spin_ns, cudaStream_t st);
 

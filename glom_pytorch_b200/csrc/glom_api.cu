@@ -6,6 +6,7 @@
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace glom {
@@ -57,6 +58,9 @@ WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, in
   w.h_off = off; off = align_up(off + w.h_bytes, 1024);
   w.c_off = off; off = align_up(off + w.c_bytes, 1024);
   for (int i = 0; i < 2; ++i) { w.nsq_off[i] = off; off = align_up(off + w.nsq_bytes, 1024); }
+  w.sched_off = off;
+  w.sched_bytes = (precision == GLOM_B200_BF16 && mlp_fused_supported(g)) ? (size_t)iters * mlp_sched_ints(g) * sizeof(int) : 0;
+  off = align_up(off + w.sched_bytes, 1024);
   w.total = off > 0 ? off : 1024;
   return w;
 }
@@ -220,6 +224,16 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
     cudaError_t e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
     if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "prep launch: %s", cudaGetErrorString(e));
+    // merged MLP kernel (dim % 256 == 0): its tile / dependency counters for every step, zeroed once per call.
+    // GLOM_B200_SPLIT_MLP=1 (diagnostics, A/B timing) keeps the three-kernel step.
+    const char* split_env = getenv("GLOM_B200_SPLIT_MLP");       // read per call: tests toggle it in-process
+    const bool split_mlp = split_env && split_env[0] == '1';
+    int* sched = nullptr;
+    if (wl.sched_bytes && !split_mlp && iters > 0) {
+      sched = reinterpret_cast<int*>(ws + wl.sched_off);
+      e = cudaMemsetAsync(sched, 0, wl.sched_bytes, st);
+      if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "scheduler counters memset: %s", cudaGetErrorString(e));
+    }
     for (int t = 0; t < iters; ++t) {
       Bf16Buffers b{};
       b.s32_in = loc(t); b.s32_out = loc(t + 1);
@@ -235,7 +249,8 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
       b.b1 = reinterpret_cast<const float*>(pw + pl.b1_off);
       b.b2 = reinterpret_cast<const float*>(pw + pl.b2_off);
       char msg[400] = "";
-      const int r = step_bf16(g, b, g_encode, di.sms, st, &g_launches, msg, sizeof(msg), &g_prof);
+      const int r = step_bf16(g, b, sched ? sched + (size_t)t * mlp_sched_ints(g) : nullptr, g_encode, di.sms, st,
+                              &g_launches, msg, sizeof(msg), &g_prof);
       if (r) return fail(r == -1 ? GLOM_B200_ERR_INVALID : GLOM_B200_ERR_CUDA, "step %d: %s", t, msg);
     }
   } else {
@@ -349,6 +364,33 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
   return 0;
 }
 
+GLOM_B200_API int glom_b200_islands(const float* states, int slabs, int side_h, int side_w, int levels, int dim, float threshold,
+                                    float* cos_right, float* cos_down, float* agreement, int32_t* labels, int32_t* num_islands,
+                                    void* stream) {
+  if (!states || !cos_right || !cos_down || !agreement || !labels || !num_islands)
+    return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
+  if (slabs < 1 || slabs > 65535 || side_h < 1 || side_w < 1 || (long long)side_h * side_w > 8192 || levels < 1 ||
+      levels > 65535 || dim < 4 || dim % 4)
+    return fail(GLOM_B200_ERR_INVALID, "islands: need 1 <= slabs, levels <= 65535, side_h * side_w <= 8192, dim %% 4 == 0");
+  if (reinterpret_cast<uintptr_t>(states) % 16) return fail(GLOM_B200_ERR_INVALID, "states must be 16-byte aligned");
+  DeviceInfo di{};
+  if (int r = device_info(&di)) return r;
+  g_launches = 0;
+  cudaError_t e = launch_islands(states, slabs, side_h, side_w, levels, dim, threshold, cos_right, cos_down, agreement, labels,
+                                 num_islands, static_cast<cudaStream_t>(stream), &g_launches);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "islands launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_mlp_schedule(const glom_b200_cfg* cfg, int batch, int num_sms, int32_t* out, int capacity,
+                                         int* num_tiles, int* delay) {
+  if (int r = check_cfg(cfg)) return r;
+  if (batch < 1 || num_sms < 2 || capacity < 0 || (capacity > 0 && !out)) return fail(GLOM_B200_ERR_INVALID, "bad arguments");
+  if (mlp_schedule_dump(make_geometry(cfg, batch), num_sms, out, capacity, num_tiles, delay))
+    return fail(GLOM_B200_ERR_INVALID, "the merged MLP kernel needs bf16 precision shapes with dim %% 256 == 0");
+  return 0;
+}
+
 GLOM_B200_API int glom_b200_clock_probe(uint64_t* out_cycles_ns, int spin_us, void* stream) {
   if (!out_cycles_ns || spin_us < 1 || spin_us > 100000) return fail(GLOM_B200_ERR_INVALID, "clock probe: bad arguments");
   cudaError_t e = launch_clock_probe(reinterpret_cast<unsigned long long*>(out_cycles_ns), (unsigned long long)spin_us * 1000ull,
@@ -365,7 +407,7 @@ GLOM_B200_API int glom_b200_profile_begin(void) {
 }
 
 GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kind, int kinds) {
-  if (!ms_by_kind || !launches_by_kind || kinds < PROF_KINDS) return fail(GLOM_B200_ERR_INVALID, "need room for %d kinds", (int)PROF_KINDS);
+  if (!ms_by_kind || !launches_by_kind || kinds < 5) return fail(GLOM_B200_ERR_INVALID, "need room for at least 5 kinds");
   for (int i = 0; i < kinds; ++i) { ms_by_kind[i] = 0.0; launches_by_kind[i] = 0; }
   g_prof.enabled = false;
   for (const Profiler::Span& s : g_prof.spans) {
@@ -373,6 +415,7 @@ GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kin
     float ms = 0.f;
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof.ev[s.a], g_prof.ev[s.b]);
     if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "profile events: %s", cudaGetErrorString(e));
+    if (s.kind >= kinds) continue;              // a caller built against an older header
     ms_by_kind[s.kind] += ms;
     launches_by_kind[s.kind] += 1;
   }

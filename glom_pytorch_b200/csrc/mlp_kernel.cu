@@ -1,0 +1,456 @@
+// Merged persistent MLP kernel of the GLOM column update for sm_100a (dim % 256 == 0).
+//
+//   mlp_kernel: one launch per Jacobi step runs BOTH grouped GEMMs of GroupedFeedForward for all levels
+//     K1 tiles  H_g   = gelu_erf(A_g . W1_g^T + b1_g)                         (glom_pytorch.py:29-30, calls :134/:136)
+//     K2 tiles  S'_l  = (S_l + C_l + [H_bu,l | H_td,l] . [W2bu_l | W2td_l]^T + b2_l) / c_l   (:31, :137, :141-142)
+//   as 256 x 256 CTA-pair tiles (tcgen05 cta_group::2, the machinery of gemm_kernel in tc_kernels.cu) drawn from ONE
+//   ordered work list by a dynamic scheduler, with per-(level, row block) dependency counters in global memory:
+//
+//   * Work list: level-major (top level last: its GEMM2 tiles cost half, which keeps the tail short); inside a
+//     level the K1 tiles of row block m (256 rows: both MLP groups, all 4d/256 column tiles) are followed by the K2
+//     tiles of row block m - delay.  Every K2 tile therefore depends only on tiles EARLIER in the list, so handing the
+//     list out in order can never deadlock, and by the time a K2 tile is drawn its producers (>= one full wave of
+//     clusters earlier) have normally retired: the hidden activations H are consumed ~10 us after they were written,
+//     while they are still in L2.  The 2 x 369 MB HBM round trip of H of the two-kernel path (K1 launch, then K2
+//     launch) becomes L2 traffic; only the eventual write-back of the dead lines remains.
+//   * Scheduler: lane 0 of a control warp of the leader CTA draws tile indices with atomicAdd and publishes them
+//     through an 8-slot shared-memory ring to the TMA / MMA / epilogue roles of BOTH CTAs of the pair (local store +
+//     mbarrier for its own CTA, st.async + complete_tx for the peer).  Tiles of very different cost (K = d for K1,
+//     8d for K2, 4d for the top level) balance themselves; there is no static-schedule quantisation.
+//   * Dependencies: each epilogue warp of a K1 tile publishes its H stores (fence) and bumps ready[level][row block];
+//     the TMA producers of a K2 tile wait (ld.acquire.gpu) for all 32 x (tiles of the row block) arrivals and cross
+//     into the async proxy (fence.proxy.async.global) before their first load of H.
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace glom {
+
+constexpr int MLP_BN = 256;
+constexpr int MLP_STAGES = 5;
+constexpr int MLP_EPI_WARPS = 16;                 // 4 TMEM lane quadrants x 4 column parts of 64
+constexpr int MLP_CTRL_WARPS = 4;                 // TMA, MMA, TMEM allocator, scheduler
+constexpr int MLP_THREADS = 32 * (MLP_EPI_WARPS + MLP_CTRL_WARPS);
+constexpr int MLP_SLOTS = 8;                      // scheduler ring
+constexpr uint32_t MLP_STAGE_BYTES = A_STAGE_BYTES + (MLP_BN / 2) * BK * 2;     // 32 KB: A (128 x 64) + half of B
+constexpr uint32_t MLP_PATCH_BYTES = 4096;        // per-warp transpose patch (K2: 32 x 32 fp32; K1: 2 KB + its bias slice)
+constexpr uint32_t MLP_TMEM_COLS = 2 * MLP_BN;    // two accumulator stages
+constexpr size_t MLP_SMEM_BYTES = 1024 + (size_t)MLP_STAGES * MLP_STAGE_BYTES + (size_t)MLP_EPI_WARPS * MLP_PATCH_BYTES + 512;
+constexpr int MLP_SEMPTY_COUNT = (MLP_EPI_WARPS + 2) + (MLP_EPI_WARPS + 1);   // leader: epilogue + TMA + MMA; peer: epilogue + TMA
+constexpr int MLP_MAX_LEVELS = 16;
+
+struct MlpParams {
+  int rows, d, L, n;
+  int num_m;                 // 256-row pair tiles
+  int nN1, nN2;              // column tiles of GEMM1 (4d / 256) and GEMM2 (d / 256)
+  int m128;                  // 128-row blocks of the (padded) hidden buffer H
+  int delay;                 // row blocks between the K1 tiles of a row block and its K2 tiles
+  int num_tiles;
+  int level_base[MLP_MAX_LEVELS + 1];   // first list index of level l
+  const float* b1;           // (G * 4d)
+  const float* b2;           // (L * d)   b2bu + b2td
+  __nv_bfloat16* h;
+  const float* s32_in;  const __nv_bfloat16* c_in;  const float* pos;
+  float* s32_out;  __nv_bfloat16* sb_out;  __nv_bfloat16* sp_out;  float* nsq_out;
+  int nparts;
+  int* counter;              // tile counter of this launch (zeroed by the caller)
+  int* ready;                // [L * num_m] K1 arrivals per (level, row block) (zeroed by the caller)
+};
+
+struct MlpTile {
+  int kind;                  // 0 = K1 (GEMM1 + GELU -> H), 1 = K2 (GEMM2 + combine -> state t+1)
+  int z;                     // K1: MLP group (2l = bottom-up l, 2l + 1 = top-down l); K2: level l
+  int l, m_blk, n_blk, num_kb;
+};
+
+__host__ __device__ __forceinline__ MlpTile mlp_decode(const MlpParams& p, int tile) {
+  int l = 0;
+  while (l + 1 < p.L && tile >= p.level_base[l + 1]) ++l;
+  const int idx = tile - p.level_base[l];
+  const int ng = (l == p.L - 1) ? 1 : 2;                // the top level has no top-down group (:137)
+  const int c1 = ng * p.nN1, c2 = p.nN2;
+  const int dl = p.delay < p.num_m ? p.delay : p.num_m;
+  int m, r;
+  bool k2;
+  if (idx < dl * c1) {                                  // head: the first `delay` row blocks have no K2 tiles behind them yet
+    m = idx / c1; r = idx - m * c1; k2 = false;
+  } else {
+    int j = idx - dl * c1;
+    const int per = c1 + c2, zone = (p.num_m - dl) * per;
+    if (j < zone) {                                     // steady state: K1 tiles of row block dl + q, then K2 tiles of q
+      const int q = j / per;
+      r = j - q * per;
+      if (r < c1) { m = dl + q; k2 = false; } else { m = q; r -= c1; k2 = true; }
+    } else {                                            // tail: K2 tiles of the last `delay` row blocks
+      j -= zone;
+      const int q = j / c2;
+      m = p.num_m - dl + q; r = j - q * c2; k2 = true;
+    }
+  }
+  MlpTile t;
+  t.l = l; t.m_blk = m;
+  if (k2) {
+    t.kind = 1; t.z = l; t.n_blk = r;
+    t.num_kb = ((l == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;
+  } else {
+    const int gi = r / p.nN1;
+    t.kind = 0; t.z = 2 * l + gi; t.n_blk = r - gi * p.nN1;
+    t.num_kb = p.d / BK;
+  }
+  return t;
+}
+
+// next tile index of the cluster's sequence (slot seq % MLP_SLOTS of the ring); -1 = no more work
+__device__ __forceinline__ int mlp_fetch(uint64_t* sfull, const volatile int* stile, uint32_t sempty_leader, uint32_t seq) {
+  const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
+  mbar_wait_cluster(&sfull[slot], ph);
+  const int tile = stile[slot];
+  // the release of the slot must not overtake the read above: make the arrive depend on the value
+  if (tile >= -1) mbar_arrive_cluster(sempty_leader + 8u * slot);
+  return tile;
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
+           const __grid_constant__ CUtensorMap map_sb,   // state shadow Sb (rows, L*d)
+           const __grid_constant__ CUtensorMap map_sp,   // Sb[:,1:]+pos shadow Sp (rows, (L-1)*d)
+           const __grid_constant__ CUtensorMap map_w1,   // W1p (G*4d, d)
+           const __grid_constant__ CUtensorMap map_h,    // H as 16 KB blocks
+           const __grid_constant__ CUtensorMap map_w2,   // W2p (L*d, 8d)
+           const MlpParams p) {
+  constexpr int STAGES = MLP_STAGES;
+  constexpr int BN = MLP_BN;
+  constexpr int PART_COLS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* patches = smem + (size_t)STAGES * MLP_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(patches + (size_t)MLP_EPI_WARPS * MLP_PATCH_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* sfull_bar = tempty_bar + 2;               // [MLP_SLOTS] own: tile index of the slot published
+  uint64_t* sempty_bar = sfull_bar + MLP_SLOTS;       // [MLP_SLOTS] leader's: every consumer of both CTAs has read it
+  int* stile = reinterpret_cast<int*>(sempty_bar + MLP_SLOTS);   // [MLP_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stile + MLP_SLOTS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int W_TMA = MLP_EPI_WARPS, W_MMA = MLP_EPI_WARPS + 1, W_ALLOC = MLP_EPI_WARPS + 2, W_SCHED = MLP_EPI_WARPS + 3;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_sb); tma_prefetch_desc(&map_sp);
+    tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_w2);
+  }
+  if (warp == W_MMA && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * MLP_EPI_WARPS); }
+    for (int i = 0; i < MLP_SLOTS; ++i) { mbar_init(&sfull_bar[i], 1); mbar_init(&sempty_bar[i], MLP_SEMPTY_COUNT); }
+    fence_barrier_init();
+  }
+  if (warp == W_ALLOC) tmem_alloc_2sm(tmem_slot, MLP_TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised + both TMEM allocations done before any cross-CTA traffic
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                  // global memory (counters included) is touched only after the previous kernel finished
+
+  const uint32_t sempty_leader = mapa_shared(smem_u32(&sempty_bar[0]), 0);
+
+  if (warp == W_SCHED) {
+    // ------------------------------------------------------------------ scheduler (leader CTA, one lane)
+    if (lane == 0 && leader) {
+      for (uint32_t seq = 0;; ++seq) {
+        const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
+        mbar_wait_cluster(&sempty_bar[slot], ph ^ 1u);        // all 35 readers of the slot's previous use are done
+        int tile = atomicAdd(p.counter, 1);
+        if (tile >= p.num_tiles) tile = -1;
+        *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
+        mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
+        const uint32_t rbar = mapa_shared(smem_u32(&sfull_bar[slot]), 1);
+        mbar_arrive_expect_tx_cluster(rbar, 4);                               // peer CTA: value + completion in one
+        st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
+        if (tile < 0) break;
+      }
+    }
+  } else if (warp == W_TMA) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint64_t pol_first = l2_policy_evict_first();
+      for (uint32_t seq = 0;; ++seq) {
+        const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+        if (tile < 0) break;
+        const MlpTile t = mlp_decode(p, tile);
+        const CUtensorMap* amap;
+        int a_col = 0, b_row;
+        const CUtensorMap* bmap;
+        if (t.kind == 0) {
+          const int l = t.l;
+          if (t.z == 0) { amap = &map_x; a_col = 0; }                          // bottom-up level 0 reads the tokens (:132)
+          else if (t.z & 1) { amap = &map_sp; a_col = l * p.d; }               // top-down l reads S[l+1]+pos (:136)
+          else { amap = &map_sb; a_col = (l - 1) * p.d; }                      // bottom-up l reads S[l-1]   (:134)
+          bmap = &map_w1;
+          b_row = t.z * 4 * p.d + t.n_blk * BN;
+        } else {
+          amap = &map_h; bmap = &map_w2;
+          b_row = t.z * p.d + t.n_blk * BN;
+          // all K1 tiles of this (level, row block) have published their part of H
+          const int need = ((t.l == p.L - 1) ? 1 : 2) * p.nN1 * 2 * MLP_EPI_WARPS;
+          const int* ctr = p.ready + t.l * p.num_m + t.m_blk;
+          if (ld_acquire_gpu(ctr) < need) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(ctr) < need) {
+              __nanosleep(64);
+              if (clock64() - t0 > GLOM_WAIT_TIMEOUT_CYCLES) {
+                printf("glom_b200: mlp_kernel dependency wait timed out (block %d level %d row block %d: %d of %d)\n",
+                       (int)blockIdx.x, t.l, t.m_blk, ld_acquire_gpu(ctr), need);
+                __trap();
+              }
+            }
+          }
+          fence_proxy_async_global();          // generic-proxy stores of H (other SMs) -> this thread's TMA loads
+        }
+        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
+        b_row += (int)cta_rank * (BN / 2);
+        const int kbg_n = 4 * p.d / BK;
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * MLP_STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * MLP_STAGE_BYTES);   // both CTAs' bytes land here
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (t.kind == 1) {
+            // block (group g, 128-row block, 64-wide k block): [H_bu,l | H_td,l] are groups 2l and 2l+1
+            const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
+            const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
+            // last use of these lines by this column tile: evict-first keeps them from displacing weights / state
+            tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, pol_first);
+          } else {
+            tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
+          }
+          tma_load_2d_2sm(sa + A_STAGE_BYTES, bmap, bar, kb * BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (uint32_t seq = 0;; ++seq) {
+        const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+        if (tile < 0) break;
+        const MlpTile t = mlp_decode(p, tile);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);      // both CTAs' epilogues drained this accumulator stage
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < t.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * MLP_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp < MLP_EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int part = warp >> 2;                // 64-column part of the tile
+    uint8_t* patch = patches + (size_t)warp * MLP_PATCH_BYTES;
+    float* bias_w = reinterpret_cast<float*>(patch + 2048);      // K1: this warp's 64 bias values (upper patch half)
+    int as = 0; uint32_t aphase = 0;
+    for (uint32_t seq = 0;; ++seq) {
+      int tile = 0;
+      if (lane == 0) tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile < 0) break;
+      const MlpTile t = mlp_decode(p, tile);
+      const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
+      const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
+      // bias of this warp's columns: fetched before the accumulator wait, so the L2 latency overlaps the MMAs
+      float4 b4k2[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      if (t.kind == 0) {
+        const float2 bv = __ldg(reinterpret_cast<const float2*>(p.b1 + (size_t)t.z * 4 * p.d + t.n_blk * BN + part * PART_COLS) + lane);
+        *reinterpret_cast<float2*>(bias_w + 2 * lane) = bv;
+        __syncwarp();
+      } else {
+        const float* bsrc = p.b2 + (size_t)t.z * p.d + t.n_blk * BN + part * PART_COLS + (lane & 7) * 4;
+        b4k2[0] = __ldg(reinterpret_cast<const float4*>(bsrc));
+        b4k2[1] = __ldg(reinterpret_cast<const float4*>(bsrc + 32));
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
+      if (t.kind == 0) {
+        // H block (group, 128-row block, k block = this warp's 64-column part): 16 KB contiguous, row pitch 64
+        const int hblk = (t.z * p.m128 + (t.m_blk * 2 + (int)cta_rank)) * (4 * p.d / BK) + t.n_blk * (BN / BK) + part;
+        __nv_bfloat16* hrow = p.h + ((size_t)hblk * BM + quad * 32) * BK;
+#pragma unroll 1
+        for (int c0 = 0; c0 < PART_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (rows_left >= 32) k1_chunk<true, false>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, 32);
+          else k1_chunk<false, false>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, rows_left);
+        }
+      } else {
+        K2Chunk kc;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0;
+        kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
+        kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
+        float rowsq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowsq[i] = 0.f;
+#pragma unroll 1
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = ci * 32;
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          const int col = t.n_blk * BN + part * PART_COLS + c0;
+          const float4 b4 = ci ? b4k2[1] : b4k2[0];
+          if (rows_left >= 32) k2_chunk<true>(v, b4, patch, kc, col, lane, 32, rowsq);
+          else k2_chunk<false>(v, b4, patch, kc, col, lane, rows_left, rowsq);
+        }
+        if ((lane & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            if (r < rows_left)
+              p.nsq_out[((size_t)(row0 + r) * p.L + t.z) * p.nparts + t.n_blk * 4 + part] = rowsq[i];
+          }
+        }
+      }
+      // release this accumulator stage to the leader's MMA issuer: one arrival per epilogue warp of either CTA
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (t.kind == 0) {
+        // publish this warp's part of H: every lane's stores ordered before the counter bump (gpu scope); the
+        // consumers read it through TMA (async proxy)
+        fence_proxy_async_global();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.ready + t.l * p.num_m + t.m_blk, 1);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
+  if (warp == W_ALLOC) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, MLP_TMEM_COLS);
+  }
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+bool mlp_fused_supported(const Geometry& g) { return g.d % 256 == 0 && g.L <= MLP_MAX_LEVELS && g.L >= 2; }
+
+size_t mlp_sched_ints(const Geometry& g) {                       // per launch: tile counter + ready[L * num_m], padded
+  const size_t n = 1 + (size_t)g.L * ((g.rows + 255) / 256);
+  return (n + 31) / 32 * 32;
+}
+
+// work-list geometry of one launch (everything mlp_decode needs)
+static void mlp_list_params(const Geometry& g, int num_sms, MlpParams* pp) {
+  MlpParams& p = *pp;
+  const int d = g.d, L = g.L, rows = g.rows;
+  p.rows = rows; p.d = d; p.L = L; p.n = g.n;
+  p.num_m = (rows + 255) / 256;
+  p.nN1 = 4 * d / MLP_BN; p.nN2 = d / MLP_BN;
+  p.m128 = (rows + BM - 1) / BM;
+  const int max_clusters = num_sms / 2;
+  // K2 tiles trail their row block's K1 tiles by at least ~1.25 waves of clusters worth of list entries
+  const int per_block = 2 * p.nN1 + p.nN2;
+  static int delay_override = -2;
+  if (delay_override == -2) { const char* e = getenv("GLOM_B200_MLP_DELAY"); delay_override = e ? atoi(e) : -1; }
+  p.delay = delay_override >= 0 ? delay_override : (5 * max_clusters / 4 + per_block - 1) / per_block;
+  if (p.delay < 1) p.delay = 1;
+  int base = 0;
+  for (int l = 0; l < L; ++l) {
+    p.level_base[l] = base;
+    base += p.num_m * (((l == L - 1) ? 1 : 2) * p.nN1 + p.nN2);
+  }
+  p.level_base[L] = base;
+  p.num_tiles = base;
+}
+
+// diagnostics / host tests: the ordered work list as (kind, z, m_blk, n_blk) quadruples
+int mlp_schedule_dump(const Geometry& g, int num_sms, int* out, int capacity, int* num_tiles, int* delay) {
+  if (!mlp_fused_supported(g)) return -1;
+  MlpParams p{};
+  mlp_list_params(g, num_sms, &p);
+  if (num_tiles) *num_tiles = p.num_tiles;
+  if (delay) *delay = p.delay;
+  for (int i = 0; i < p.num_tiles && i < capacity; ++i) {
+    const MlpTile t = mlp_decode(p, i);
+    out[4 * i] = t.kind; out[4 * i + 1] = t.z; out[4 * i + 2] = t.m_blk; out[4 * i + 3] = t.n_blk;
+  }
+  return 0;
+}
+
+int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn enc, int num_sms,
+                        cudaStream_t st, int* launches, char* err, size_t errlen, Profiler* prof) {
+  const int d = g.d, L = g.L, rows = g.rows;
+  const int m128 = (rows + BM - 1) / BM;
+  CUtensorMap mh, mx, msb, msp, mw1, mw2;
+  if (!map2d(enc, &mh, b.h, (uint64_t)g.G * m128 * (4 * d / BK) * BM, BK, BM, err, errlen, "H")) return -3;
+  if (!map2d(enc, &mx, b.xb, rows, d, BM, err, errlen, "Xb")) return -3;
+  if (!map2d(enc, &msb, b.sb_in, rows, (uint64_t)L * d, BM, err, errlen, "Sb")) return -3;
+  if (!map2d(enc, &msp, b.sp_in, rows, (uint64_t)(L - 1) * d, BM, err, errlen, "Sp")) return -3;
+  if (!map2d(enc, &mw1, b.w1, (uint64_t)g.G * 4 * d, d, 128, err, errlen, "W1p")) return -3;
+  if (!map2d(enc, &mw2, b.w2, (uint64_t)L * d, (uint64_t)8 * d, 128, err, errlen, "W2p")) return -3;
+  MlpParams p{};
+  mlp_list_params(g, num_sms, &p);
+  const int max_clusters = num_sms / 2;
+  p.b1 = b.b1; p.b2 = b.b2; p.h = b.h;
+  p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+  p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+  p.counter = sched; p.ready = sched + 1;
+
+  static SmemOptIn optin;
+  if (cudaError_t e = optin.ensure(mlp_kernel, MLP_SMEM_BYTES)) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(mlp_kernel): %s", cudaGetErrorString(e));
+    return -3;
+  }
+  const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(MLP_THREADS);
+  cfg.dynamicSmemBytes = MLP_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  ProfScope scope(prof, PROF_MLP, st);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_kernel, mx, msb, msp, mw1, mh, mw2, p);
+  if (launches) ++*launches;
+  if (e != cudaSuccess) { snprintf(err, errlen, "mlp_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  return 0;
+}
+
+}  // namespace glom

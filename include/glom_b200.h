@@ -156,11 +156,34 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
  * kernel the forward/tokenize calls of THIS thread enqueue is bracketed by CUDA events on the
  * launch stream (no synchronisation is added to the calls).  _end waits for those events and
  * returns summed milliseconds and launch counts per kernel kind:
- *   0 consensus attention, 1 GEMM1+GELU, 2 GEMM2+combine, 3 state prologue, 4 tokeniser.
- * `kinds` is the capacity of both arrays (>= 5). */
-#define GLOM_B200_PROFILE_KINDS 5
+ *   0 consensus attention, 1 GEMM1+GELU, 2 GEMM2+combine, 3 state prologue, 4 tokeniser,
+ *   5 merged persistent MLP kernel (GEMM1+GELU and GEMM2+combine tiles of one step in one launch, dim % 256 == 0).
+ * `kinds` is the capacity of both arrays (>= 5; kinds beyond the capacity are dropped). */
+#define GLOM_B200_PROFILE_KINDS 6
 GLOM_B200_API int glom_b200_profile_begin(void);
 GLOM_B200_API int glom_b200_profile_end(double* ms_by_kind, int* launches_by_kind, int kinds);
+
+/* Island analytics on column states (the consumer of return_all the reference's README.md:34-36
+ * describes: "all the level data across iterations for clustering, from which one can inspect for the theorized
+ * islands").  states: `slabs` contiguous (side_h * side_w, levels, dim) fp32 state slabs, e.g. the (iters+1) * B slabs of
+ * glom_b200_forward(return_all = 1).  Per (slab, level), on the patch grid (patch i = h * side_w + w):
+ *   cos_right / cos_down (slabs, levels, n)  cosine similarity with the right / lower neighbour (0 where there is none)
+ *   agreement            (slabs, levels, n)  mean cosine similarity with the existing 4-neighbours
+ *   labels               (slabs, levels, n)  island id = smallest patch index of the 4-connected component in the graph
+ *                                            of neighbour pairs with cosine similarity >= threshold
+ *   num_islands          (slabs, levels)     number of such components
+ * HBM-bound CUDA-core kernels (3 dot products per patch, no Gram matrix); all outputs device memory of the caller. */
+GLOM_B200_API int glom_b200_islands(const float* states, int slabs, int side_h, int side_w, int levels, int dim, float threshold,
+                                    float* cos_right, float* cos_down, float* agreement, int32_t* labels,
+                                    int32_t* num_islands, void* stream);
+
+/* Diagnostics (host only, no GPU needed): the ordered work list of the merged persistent MLP kernel (dim % 256 == 0) for
+ * (cfg, batch) on a device with `num_sms` SMs, as (kind, z, m_blk, n_blk) quadruples: kind 0 = GEMM1+GELU tile of MLP
+ * group z (2l = bottom-up l, 2l+1 = top-down l), kind 1 = GEMM2+combine tile of level z; m_blk = 256-row block,
+ * n_blk = 256-column block.  Writes min(capacity, *num_tiles) entries; *delay = row blocks by which a row block's GEMM2
+ * tiles trail its GEMM1 tiles.  Every kind-1 tile appears after all kind-0 tiles it depends on (tests check it). */
+GLOM_B200_API int glom_b200_mlp_schedule(const glom_b200_cfg* cfg, int batch, int num_sms, int32_t* out, int capacity,
+                                         int* num_tiles, int* delay);
 
 /* Measurement aid (bench.py): one device thread spins for `spin_us` microseconds of %globaltimer and writes
  * {SM cycles elapsed, nanoseconds elapsed} to out_cycles_ns[0..1] (device memory, 16 bytes): cycles / ns is the SM

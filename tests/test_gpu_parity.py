@@ -397,6 +397,30 @@ def test_packed_weight_cache_follows_the_parameters():
         assert not torch.equal(m(x, iters=2), c)            # training mode sees .data edits immediately
 
 
+@pytest.mark.parametrize("spec", [(256, 3, 32, 4, 3, 3), (512, 6, 224, 14, 3, 4), (512, 2, 32, 4, 1, 2), (1024, 8, 384, 16, 1, 2),
+                                  (256, 4, 64, 4, 9, 5)],
+                         ids=["d256_rows192", "config2_dims_B3", "d512_L2_rows64", "config4_dims_B1", "d256_rows2304"])
+def test_merged_mlp_kernel_is_bit_identical_to_the_three_kernel_step(spec, monkeypatch):
+    """dim % 256 == 0: the step is consensus + ONE persistent MLP kernel (mlp_kernel.cu: GEMM1+GELU and GEMM2+combine
+    tiles from a dynamically scheduled list with dependency counters).  Same tiles, same accumulation order as the
+    three-kernel step (GLOM_B200_SPLIT_MLP=1), so every time step must agree bit for bit; run twice to catch races."""
+    dim, L, isz, p, B, T = spec
+    torch.manual_seed(21)
+    m = G.Glom(dim=dim, levels=L, image_size=isz, patch_size=p).to(DEV).eval()
+    img = torch.randn(B, 3, isz, isz, generator=torch.Generator().manual_seed(22)).to(DEV)
+    with torch.no_grad():
+        monkeypatch.setenv("GLOM_B200_SPLIT_MLP", "1")
+        ref = m(img, iters=T, return_all=True)
+        launches_split = m.last_launches
+        monkeypatch.delenv("GLOM_B200_SPLIT_MLP")
+        for _ in range(2):
+            out = m(img, iters=T, return_all=True)
+            assert torch.equal(out, ref)
+        assert m.last_launches == launches_split - T          # one launch fewer per iteration
+        last = m(img, iters=T)                                 # ping-pong (not return_all) addressing
+        assert torch.equal(last, ref[-1])
+
+
 def test_clock_probe_reports_a_plausible_sm_clock():
     buf = torch.zeros(2, dtype=torch.int64, device=DEV)
     _native.clock_probe(buf.data_ptr(), 200, torch.cuda.current_stream().cuda_stream)
