@@ -56,6 +56,7 @@ struct MlpParams {
   int nparts;
   int* counter;              // tile counter of this launch (zeroed by the caller)
   int* ready;                // [L * num_m] K1 arrivals per (level, row block) (zeroed by the caller)
+  unsigned long long* dbg;   // DBG instantiation only: 16 cycle counters per CTA (GLOM_B200_MLP_DBG=1)
 };
 
 struct MlpTile {
@@ -104,13 +105,23 @@ __host__ __device__ __forceinline__ MlpTile mlp_decode(const MlpParams& p, int t
 // next tile index of the cluster's sequence (slot seq % MLP_SLOTS of the ring); -1 = no more work
 __device__ __forceinline__ int mlp_fetch(uint64_t* sfull, const volatile int* stile, uint32_t sempty_leader, uint32_t seq) {
   const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
-  mbar_wait_cluster(&sfull[slot], ph);
+  // plain (cta-scope) wait in both CTAs: the leader's slot is written by a thread of the same CTA, the peer's by
+  // st.async, whose data is visible to whoever observes the barrier's transaction count complete (like TMA data)
+  mbar_wait(&sfull[slot], ph);
   const int tile = stile[slot];
   // the release of the slot must not overtake the read above: make the arrive depend on the value
   if (tile >= -1) mbar_arrive_cluster(sempty_leader + 8u * slot);
   return tile;
 }
 
+// cycles spent inside `stmt` added to `acc` (DBG builds only)
+#define MLP_TIMED(acc, stmt)                               \
+  do {                                                     \
+    if (DBG) { const long long t_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t_); } \
+    else { stmt; }                                         \
+  } while (0)
+
+template <bool DBG>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
            const __grid_constant__ CUtensorMap map_sb,   // state shadow Sb (rows, L*d)
@@ -160,14 +171,18 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
   pdl_wait();                  // global memory (counters included) is touched only after the previous kernel finished
 
   const uint32_t sempty_leader = mapa_shared(smem_u32(&sempty_bar[0]), 0);
+  const long long k_t0 = DBG ? clock64() : 0;
+  unsigned long long dw0 = 0, dw1 = 0, dw2 = 0, dw3 = 0, dw4 = 0;     // per-role wait / work counters (DBG)
+  unsigned long long* dbg = DBG ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 
   if (warp == W_SCHED) {
     // ------------------------------------------------------------------ scheduler (leader CTA, one lane)
     if (lane == 0 && leader) {
       for (uint32_t seq = 0;; ++seq) {
         const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
-        mbar_wait_cluster(&sempty_bar[slot], ph ^ 1u);        // all 35 readers of the slot's previous use are done
-        int tile = atomicAdd(p.counter, 1);
+        MLP_TIMED(dw0, mbar_wait(&sempty_bar[slot], ph ^ 1u));     // all 35 readers of the slot's previous use are done
+        int tile;
+        MLP_TIMED(dw1, tile = atomicAdd(p.counter, 1));
         if (tile >= p.num_tiles) tile = -1;
         *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
         mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
@@ -176,6 +191,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
         if (tile < 0) break;
       }
+      if (DBG) { dbg[0] = dw0; dbg[1] = dw1; }
     }
   } else if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -183,7 +199,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       int stage = 0; uint32_t phase = 0;
       const uint64_t pol_first = l2_policy_evict_first();
       for (uint32_t seq = 0;; ++seq) {
-        const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+        int tile;
+        MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
         if (tile < 0) break;
         const MlpTile t = mlp_decode(p, tile);
         const CUtensorMap* amap;
@@ -204,6 +221,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           const int* ctr = p.ready + t.l * p.num_m + t.m_blk;
           if (ld_acquire_gpu(ctr) < need) {
             const long long t0 = clock64();
+            if (DBG) ++dw3;
             while (ld_acquire_gpu(ctr) < need) {
               __nanosleep(64);
               if (clock64() - t0 > GLOM_WAIT_TIMEOUT_CYCLES) {
@@ -212,6 +230,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
                 __trap();
               }
             }
+            if (DBG) dw1 += (unsigned long long)(clock64() - t0);
           }
           fence_proxy_async_global();          // generic-proxy stores of H (other SMs) -> this thread's TMA loads
         }
@@ -219,7 +238,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         b_row += (int)cta_rank * (BN / 2);
         const int kbg_n = 4 * p.d / BK;
         for (int kb = 0; kb < t.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          MLP_TIMED(dw2, mbar_wait(&empty_bar[stage], phase ^ 1));
           uint8_t* sa = smem + (size_t)stage * MLP_STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * MLP_STAGE_BYTES);   // both CTAs' bytes land here
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -236,6 +255,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (DBG) { dbg[2] = dw0; dbg[3] = dw1; dbg[4] = dw2; dbg[15] = dw3; }
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -244,14 +264,15 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (uint32_t seq = 0;; ++seq) {
-        const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+        int tile;
+        MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
         if (tile < 0) break;
         const MlpTile t = mlp_decode(p, tile);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);      // both CTAs' epilogues drained this accumulator stage
+        MLP_TIMED(dw1, mbar_wait(&tempty_bar[as], aphase ^ 1));      // both CTAs' epilogues drained this accumulator stage
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < t.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          MLP_TIMED(dw2, mbar_wait(&full_bar[stage], phase));
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * MLP_STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
@@ -266,7 +287,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         }
         umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
         if (++as == 2) { as = 0; aphase ^= 1; }
+        if (DBG) ++dw3;
       }
+      if (DBG) { dbg[5] = dw0; dbg[6] = dw1; dbg[7] = dw2; dbg[14] = dw3; }
     }
   } else if (warp < MLP_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (16 warps)
@@ -277,7 +300,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
     int as = 0; uint32_t aphase = 0;
     for (uint32_t seq = 0;; ++seq) {
       int tile = 0;
-      if (lane == 0) tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
+      if (lane == 0) MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
       tile = __shfl_sync(0xffffffffu, tile, 0);
       if (tile < 0) break;
       const MlpTile t = mlp_decode(p, tile);
@@ -294,8 +317,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         b4k2[0] = __ldg(reinterpret_cast<const float4*>(bsrc));
         b4k2[1] = __ldg(reinterpret_cast<const float4*>(bsrc + 32));
       }
-      mbar_wait(&tfull_bar[as], aphase);
+      MLP_TIMED(dw1, mbar_wait(&tfull_bar[as], aphase));
       tc_fence_after_sync();
+      const long long e_t0 = DBG ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
       if (t.kind == 0) {
         // H block (group, 128-row block, k block = this warp's 64-column part): 16 KB contiguous, row pitch 64
@@ -342,14 +366,18 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (DBG) { if (t.kind == 0) dw2 += (unsigned long long)(clock64() - e_t0); else dw3 += (unsigned long long)(clock64() - e_t0); }
       if (t.kind == 0) {
-        // publish this warp's part of H: every lane's stores ordered before the counter bump (gpu scope); the
-        // consumers read it through TMA (async proxy)
-        fence_proxy_async_global();
-        __threadfence();
+        // publish this warp's part of H: the lanes' stores are ordered before lane 0's release by the warp barrier
+        // (cumulativity), so ONE gpu-scope release per warp and tile suffices -- a __threadfence() in every lane is an
+        // sc fence and was measured ~15 us per tile here.  The consumer crosses into the async proxy on its side.
         __syncwarp();
-        if (lane == 0) atomicAdd(p.ready + t.l * p.num_m + t.m_blk, 1);
+        if (lane == 0) MLP_TIMED(dw4, red_release_gpu_add(p.ready + t.l * p.num_m + t.m_blk, 1));
       }
+    }
+    if (DBG && warp == 0 && lane == 0) {
+      dbg[8] = dw0; dbg[9] = dw1; dbg[10] = dw2; dbg[11] = dw3; dbg[12] = dw4;
+      dbg[13] = (unsigned long long)(clock64() - k_t0);
     }
   }
 
@@ -429,8 +457,17 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
   p.counter = sched; p.ready = sched + 1;
 
-  static SmemOptIn optin;
-  if (cudaError_t e = optin.ensure(mlp_kernel, MLP_SMEM_BYTES)) {
+  // GLOM_B200_MLP_DBG=1 (diagnostics): the instrumented instantiation, synchronised and summarised on stderr for the
+  // first launches of the process.  Never set in production: it allocates a small device buffer and blocks the stream.
+  static int dbg_mode = -1;
+  static unsigned long long* dbg_buf = nullptr;
+  static int dbg_left = 4;
+  if (dbg_mode < 0) { const char* e = getenv("GLOM_B200_MLP_DBG"); dbg_mode = (e && e[0] == '1') ? 1 : 0; }
+  const bool dbg = dbg_mode == 1 && dbg_left > 0;
+  if (dbg && !dbg_buf && cudaMalloc(&dbg_buf, (size_t)num_sms * 16 * sizeof(unsigned long long)) != cudaSuccess) return -3;
+  if (dbg) { cudaMemsetAsync(dbg_buf, 0, (size_t)num_sms * 16 * sizeof(unsigned long long), st); p.dbg = dbg_buf; }
+  static SmemOptIn optin, optin_dbg;
+  if (cudaError_t e = dbg ? optin_dbg.ensure(mlp_kernel<true>, MLP_SMEM_BYTES) : optin.ensure(mlp_kernel<false>, MLP_SMEM_BYTES)) {
     snprintf(err, errlen, "cudaFuncSetAttribute(mlp_kernel): %s", cudaGetErrorString(e));
     return -3;
   }
@@ -446,10 +483,35 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
-  ProfScope scope(prof, PROF_MLP, st);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_kernel, mx, msb, msp, mw1, mh, mw2, p);
+  cudaError_t e;
+  {
+    ProfScope scope(prof, PROF_MLP, st);
+    e = dbg ? cudaLaunchKernelEx(&cfg, mlp_kernel<true>, mx, msb, msp, mw1, mh, mw2, p)
+            : cudaLaunchKernelEx(&cfg, mlp_kernel<false>, mx, msb, msp, mw1, mh, mw2, p);
+  }
   if (launches) ++*launches;
   if (e != cudaSuccess) { snprintf(err, errlen, "mlp_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  if (dbg) {
+    --dbg_left;
+    static const char* names[16] = {"sched: wait ring slot free", "sched: atomicAdd", "tma: fetch tile", "tma: dependency wait",
+                                    "tma: wait smem slot", "mma: fetch tile", "mma: wait accumulator free", "mma: wait operands",
+                                    "epi w0: fetch tile", "epi w0: wait accumulator", "epi w0: K1 tiles work", "epi w0: K2 tiles work",
+                                    "epi w0: publish (release)", "epi w0: kernel total", "mma: tiles", "tma: dependency waits (count)"};
+    std::vector<unsigned long long> h((size_t)num_sms * 16);
+    if (cudaStreamSynchronize(st) == cudaSuccess &&
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[mlp_kernel dbg] %d tiles, delay %d row blocks, %d clusters; cycles per CTA: mean (max)\n", p.num_tiles, p.delay, clusters);
+      for (int k = 0; k < 16; ++k) {
+        double sum = 0, mx_ = 0; int cnt = 0;
+        for (int c = 0; c < 2 * clusters; ++c) {
+          const double v = (double)h[(size_t)c * 16 + k];
+          if ((k == 0 || k == 1 || (k >= 5 && k <= 7) || k == 14) && (c & 1)) continue;     // leader-only roles
+          sum += v; if (v > mx_) mx_ = v; ++cnt;
+        }
+        fprintf(stderr, "[mlp_kernel dbg]   %-32s %12.0f (%12.0f)\n", names[k], cnt ? sum / cnt : 0.0, mx_);
+      }
+    }
+  }
   return 0;
 }
 

@@ -183,6 +183,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_clust
 }
 // generic-proxy accesses to global memory <-> async-proxy (TMA) accesses to the same locations
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// counter += v with release semantics at gpu scope: everything that happened before it in this thread -- and, by
+// cumulativity, in threads that synchronised with it (bar.warp.sync, mbarrier) -- is visible to a thread that
+// observes the new value with ld.acquire.gpu.  One MEMBAR.ALL.GPU in the executing thread only.
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

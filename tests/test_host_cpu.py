@@ -156,3 +156,51 @@ def test_merged_mlp_kernel_work_list_is_complete_and_ordered(dim, L, n, batch, s
             assert done.get((z, m), 0) == (1 if z == L - 1 else 2) * nN1, (z, m)
     # the top level (half-cost GEMM2 tiles) closes the list
     assert tiles[-1][0] == 1 and tiles[-1][1] == L - 1
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from glom_pytorch_b200.dp import allreduce_gradients, broadcast_parameters
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # deliberately different init per rank
+    m = G.Glom(dim=64, levels=3, image_size=28, patch_size=7)
+    broadcast_parameters(m, src=0)
+    ref = [p.detach().clone() for p in m.parameters()]
+    gens = torch.Generator().manual_seed(7)
+    for i, p in enumerate(m.parameters()):              # rank r holds gradient (r + 1) * base_i; init_levels has none on rank 1
+        base = torch.randn(p.shape, generator=gens)
+        p.grad = None if (rank == 1 and i == 0) else (rank + 1) * base
+    calls = allreduce_gradients(m, bucket_bytes=64 << 10)
+    gens = torch.Generator().manual_seed(7)
+    err = 0.0
+    for i, p in enumerate(m.parameters()):
+        base = torch.randn(p.shape, generator=gens)
+        want = base * (1.0 / 2.0 if i == 0 else 1.5)    # mean of (1, 2) * base; param 0: (1, 0) * base
+        err = max(err, float((p.grad - want).abs().max()))
+    same = all(torch.equal(a, b) for a, b in zip(ref, [p.detach() for p in m.parameters()]))
+    t = torch.tensor([float(ref[3].sum())])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t2 = torch.tensor([float(ref[3].sum())])
+    dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put((err, calls, same, float(t.item() - t2.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_two_ranks_gloo():
+    """the only collective of the path -- bucketed gradient averaging over the ranks (NCCL on the
+    box, gloo here), incl. a parameter that has no gradient on one rank, and the setup-time parameter broadcast."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, calls, same, spread = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err <= 1e-6 and calls >= 2 and same and spread == 0.0
