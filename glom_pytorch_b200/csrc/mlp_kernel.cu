@@ -13,13 +13,19 @@
 //     clusters earlier) have normally retired: the hidden activations H are consumed ~10 us after they were written,
 //     while they are still in L2.  The 2 x 369 MB HBM round trip of H of the two-kernel path (K1 launch, then K2
 //     launch) becomes L2 traffic; only the eventual write-back of the dead lines remains.
-//   * Scheduler: lane 0 of a control warp of the leader CTA draws tile indices with atomicAdd and publishes them
-//     through an 8-slot shared-memory ring to the TMA / MMA / epilogue roles of BOTH CTAs of the pair (local store +
-//     mbarrier for its own CTA, st.async + complete_tx for the peer).  Tiles of very different cost (K = d for K1,
-//     8d for K2, 4d for the top level) balance themselves; there is no static-schedule quantisation.
-//   * Dependencies: each epilogue warp of a K1 tile publishes its H stores (fence) and bumps ready[level][row block];
-//     the TMA producers of a K2 tile wait (ld.acquire.gpu) for all 32 x (tiles of the row block) arrivals and cross
-//     into the async proxy (fence.proxy.async.global) before their first load of H.
+//   * Scheduler: the leader CTA's TMA producer lane draws the next tile index with atomicAdd while it issues the last
+//     loads of the current tile (a claimed tile starts loading ~1-2 us later; claiming further ahead was measured to
+//     wreck the dependency order: a cluster busy with a 20 us K2 tile sat on K1 tiles other clusters waited for) and
+//     publishes it through an 8-slot shared-memory ring to the MMA / epilogue / publisher roles of BOTH CTAs of the pair
+//     and to the peer's TMA lane (local store + mbarrier for its own CTA, st.async + complete_tx for the peer).
+//     Tiles of very different cost (K = d for K1, 8d for K2, 4d for the top level) balance themselves; there is no
+//     static-schedule quantisation.
+//   * Dependencies: the 16 epilogue warps of a CTA arrive on a shared-memory mbarrier once their stores of a tile are
+//     issued; one publisher lane per CTA turns that into ONE gpu-scope release (red.release.gpu.add on
+//     ready[level][row block]) per CTA and K1 tile, off the epilogue warps' critical path (cumulativity: stores ->
+//     warp barrier -> mbarrier arrive / wait -> release).  The TMA producers of a K2 tile wait (ld.acquire.gpu) for all
+//     2 x (K1 tiles of the row block) arrivals and cross into the async proxy (fence.proxy.async.global) before their
+//     first load of H.
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -30,14 +36,15 @@ namespace glom {
 constexpr int MLP_BN = 256;
 constexpr int MLP_STAGES = 5;
 constexpr int MLP_EPI_WARPS = 16;                 // 4 TMEM lane quadrants x 4 column parts of 64
-constexpr int MLP_CTRL_WARPS = 4;                 // TMA, MMA, TMEM allocator, scheduler
+constexpr int MLP_CTRL_WARPS = 4;                 // TMA (+ scheduler in the leader), MMA, TMEM allocator, publisher
 constexpr int MLP_THREADS = 32 * (MLP_EPI_WARPS + MLP_CTRL_WARPS);
 constexpr int MLP_SLOTS = 8;                      // scheduler ring
 constexpr uint32_t MLP_STAGE_BYTES = A_STAGE_BYTES + (MLP_BN / 2) * BK * 2;     // 32 KB: A (128 x 64) + half of B
 constexpr uint32_t MLP_PATCH_BYTES = 4096;        // per-warp transpose patch (K2: 32 x 32 fp32; K1: 2 KB + its bias slice)
 constexpr uint32_t MLP_TMEM_COLS = 2 * MLP_BN;    // two accumulator stages
 constexpr size_t MLP_SMEM_BYTES = 1024 + (size_t)MLP_STAGES * MLP_STAGE_BYTES + (size_t)MLP_EPI_WARPS * MLP_PATCH_BYTES + 512;
-constexpr int MLP_SEMPTY_COUNT = (MLP_EPI_WARPS + 2) + (MLP_EPI_WARPS + 1);   // leader: epilogue + TMA + MMA; peer: epilogue + TMA
+constexpr int MLP_SEMPTY_COUNT = (MLP_EPI_WARPS + 2) + (MLP_EPI_WARPS + 2);   // leader: epilogue + MMA + publisher; peer: epilogue + TMA + publisher
+constexpr int MLP_CLAIM_AHEAD_KB = 4;             // the next tile is claimed this many k-blocks before the current tile's last load
 constexpr int MLP_MAX_LEVELS = 16;
 
 struct MlpParams {
@@ -142,7 +149,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* sfull_bar = tempty_bar + 2;               // [MLP_SLOTS] own: tile index of the slot published
   uint64_t* sempty_bar = sfull_bar + MLP_SLOTS;       // [MLP_SLOTS] leader's: every consumer of both CTAs has read it
-  int* stile = reinterpret_cast<int*>(sempty_bar + MLP_SLOTS);   // [MLP_SLOTS]
+  uint64_t* pub_bar = sempty_bar + MLP_SLOTS;         // [2] own: the 16 epilogue warps issued their stores of the tile in stage `as`
+  int* stile = reinterpret_cast<int*>(pub_bar + 2);   // [MLP_SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stile + MLP_SLOTS);
 
   const int warp = threadIdx.x >> 5;
@@ -157,7 +165,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
   }
   if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * MLP_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * MLP_EPI_WARPS); mbar_init(&pub_bar[i], MLP_EPI_WARPS); }
     for (int i = 0; i < MLP_SLOTS; ++i) { mbar_init(&sfull_bar[i], 1); mbar_init(&sempty_bar[i], MLP_SEMPTY_COUNT); }
     fence_barrier_init();
   }
@@ -176,20 +184,18 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
   unsigned long long* dbg = DBG ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 
   if (warp == W_SCHED) {
-    // ------------------------------------------------------------------ scheduler (leader CTA, one lane)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ publisher (both CTAs, one lane)
+    // once all 16 epilogue warps of this CTA have issued their stores of a K1 tile: one gpu-scope release of the
+    // (level, row block) counter for the whole CTA
+    if (lane == 0) {
+      int as = 0; uint32_t aphase = 0;
       for (uint32_t seq = 0;; ++seq) {
-        const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
-        MLP_TIMED(dw0, mbar_wait(&sempty_bar[slot], ph ^ 1u));     // all 35 readers of the slot's previous use are done
-        int tile;
-        MLP_TIMED(dw1, tile = atomicAdd(p.counter, 1));
-        if (tile >= p.num_tiles) tile = -1;
-        *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
-        mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
-        const uint32_t rbar = mapa_shared(smem_u32(&sfull_bar[slot]), 1);
-        mbar_arrive_expect_tx_cluster(rbar, 4);                               // peer CTA: value + completion in one
-        st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
+        const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
         if (tile < 0) break;
+        const MlpTile t = mlp_decode(p, tile);
+        MLP_TIMED(dw0, mbar_wait(&pub_bar[as], aphase));
+        if (t.kind == 0) MLP_TIMED(dw1, red_release_gpu_add(p.ready + t.l * p.num_m + t.m_blk, 1));
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
       if (DBG) { dbg[0] = dw0; dbg[1] = dw1; }
     }
@@ -198,10 +204,29 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint64_t pol_first = l2_policy_evict_first();
+      // leader: draws the tile index and publishes it to the ring (both CTAs); peer: reads the ring like everyone else
+      uint32_t pub_seq = 0;
+      auto claim = [&]() -> int {
+        int tile = atomicAdd(p.counter, 1);
+        if (tile >= p.num_tiles) tile = -1;
+        const uint32_t slot = pub_seq % MLP_SLOTS, ph = (pub_seq / MLP_SLOTS) & 1u;
+        mbar_wait(&sempty_bar[slot], ph ^ 1u);                  // all 36 readers of the slot's previous use are done
+        *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
+        mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
+        const uint32_t rbar = mapa_shared(smem_u32(&sfull_bar[slot]), 1);
+        mbar_arrive_expect_tx_cluster(rbar, 4);                               // peer CTA: value + completion in one
+        st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
+        ++pub_seq;
+        return tile;
+      };
+      int next_tile = -2;
+      if (leader) MLP_TIMED(dw0, next_tile = claim());
       for (uint32_t seq = 0;; ++seq) {
         int tile;
-        MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
+        if (leader) tile = next_tile;
+        else MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
         if (tile < 0) break;
+        next_tile = -2;
         const MlpTile t = mlp_decode(p, tile);
         const CUtensorMap* amap;
         int a_col = 0, b_row;
@@ -217,7 +242,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           amap = &map_h; bmap = &map_w2;
           b_row = t.z * p.d + t.n_blk * BN;
           // all K1 tiles of this (level, row block) have published their part of H
-          const int need = ((t.l == p.L - 1) ? 1 : 2) * p.nN1 * 2 * MLP_EPI_WARPS;
+          const int need = ((t.l == p.L - 1) ? 1 : 2) * p.nN1 * 2;              // one arrival per CTA and K1 tile
           const int* ctr = p.ready + t.l * p.num_m + t.m_blk;
           if (ld_acquire_gpu(ctr) < need) {
             const long long t0 = clock64();
@@ -237,7 +262,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
         b_row += (int)cta_rank * (BN / 2);
         const int kbg_n = 4 * p.d / BK;
+        const int claim_kb = t.num_kb > MLP_CLAIM_AHEAD_KB ? t.num_kb - MLP_CLAIM_AHEAD_KB : 0;
         for (int kb = 0; kb < t.num_kb; ++kb) {
+          if (leader && kb == claim_kb) MLP_TIMED(dw0, next_tile = claim());   // late look-ahead: see the header
           MLP_TIMED(dw2, mbar_wait(&empty_bar[stage], phase ^ 1));
           uint8_t* sa = smem + (size_t)stage * MLP_STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * MLP_STAGE_BYTES);   // both CTAs' bytes land here
@@ -364,16 +391,14 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       // release this accumulator stage to the leader's MMA issuer: one arrival per epilogue warp of either CTA
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (lane == 0) {
+        mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+        // this warp's stores of the tile are issued: tell the CTA's publisher lane (it releases them at gpu scope for
+        // K1 tiles; the lanes' stores are ordered before lane 0's arrive by the warp barrier above)
+        mbar_arrive(&pub_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (DBG) { if (t.kind == 0) dw2 += (unsigned long long)(clock64() - e_t0); else dw3 += (unsigned long long)(clock64() - e_t0); }
-      if (t.kind == 0) {
-        // publish this warp's part of H: the lanes' stores are ordered before lane 0's release by the warp barrier
-        // (cumulativity), so ONE gpu-scope release per warp and tile suffices -- a __threadfence() in every lane is an
-        // sc fence and was measured ~15 us per tile here.  The consumer crosses into the async proxy on its side.
-        __syncwarp();
-        if (lane == 0) MLP_TIMED(dw4, red_release_gpu_add(p.ready + t.l * p.num_m + t.m_blk, 1));
-      }
     }
     if (DBG && warp == 0 && lane == 0) {
       dbg[8] = dw0; dbg[9] = dw1; dbg[10] = dw2; dbg[11] = dw3; dbg[12] = dw4;
@@ -409,11 +434,12 @@ static void mlp_list_params(const Geometry& g, int num_sms, MlpParams* pp) {
   p.nN1 = 4 * d / MLP_BN; p.nN2 = d / MLP_BN;
   p.m128 = (rows + BM - 1) / BM;
   const int max_clusters = num_sms / 2;
-  // K2 tiles trail their row block's K1 tiles by at least ~1.25 waves of clusters worth of list entries
+  // K2 tiles trail their row block's K1 tiles by ~3 waves of clusters worth of list entries: a claimed K1 tile retires
+  // (loads, MMAs, epilogue, release) within ~10 us, during which the chip claims ~2.5 waves of tiles
   const int per_block = 2 * p.nN1 + p.nN2;
   static int delay_override = -2;
   if (delay_override == -2) { const char* e = getenv("GLOM_B200_MLP_DELAY"); delay_override = e ? atoi(e) : -1; }
-  p.delay = delay_override >= 0 ? delay_override : (5 * max_clusters / 4 + per_block - 1) / per_block;
+  p.delay = delay_override >= 0 ? delay_override : (3 * max_clusters + per_block - 1) / per_block;
   if (p.delay < 1) p.delay = 1;
   int base = 0;
   for (int l = 0; l < L; ++l) {
@@ -493,7 +519,7 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   if (e != cudaSuccess) { snprintf(err, errlen, "mlp_kernel launch: %s", cudaGetErrorString(e)); return -3; }
   if (dbg) {
     --dbg_left;
-    static const char* names[16] = {"sched: wait ring slot free", "sched: atomicAdd", "tma: fetch tile", "tma: dependency wait",
+    static const char* names[16] = {"pub: wait epilogue stores", "pub: release", "tma: claim / fetch tile", "tma: dependency wait",
                                     "tma: wait smem slot", "mma: fetch tile", "mma: wait accumulator free", "mma: wait operands",
                                     "epi w0: fetch tile", "epi w0: wait accumulator", "epi w0: K1 tiles work", "epi w0: K2 tiles work",
                                     "epi w0: publish (release)", "epi w0: kernel total", "mma: tiles", "tma: dependency waits (count)"};
@@ -505,7 +531,7 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
         double sum = 0, mx_ = 0; int cnt = 0;
         for (int c = 0; c < 2 * clusters; ++c) {
           const double v = (double)h[(size_t)c * 16 + k];
-          if ((k == 0 || k == 1 || (k >= 5 && k <= 7) || k == 14) && (c & 1)) continue;     // leader-only roles
+          if (((k >= 5 && k <= 7) || k == 14) && (c & 1)) continue;     // leader-only roles
           sum += v; if (v > mx_) mx_ = v; ++cnt;
         }
         fprintf(stderr, "[mlp_kernel dbg]   %-32s %12.0f (%12.0f)\n", names[k], cnt ? sum / cnt : 0.0, mx_);

@@ -14,7 +14,7 @@ PY
 }
 ab GLOM_B200_SPLIT_MLP=1
 ab GLOM_B200_SPLIT_MLP=0
-ab GLOM_B200_SPLIT_MLP=0 GLOM_B200_MLP_DELAY=3
-ab GLOM_B200_SPLIT_MLP=0 GLOM_B200_MLP_DELAY=10
+ab GLOM_B200_SPLIT_MLP=0 GLOM_B200_MLP_DELAY=6
+ab GLOM_B200_SPLIT_MLP=0 GLOM_B200_MLP_DELAY=24
 ( GLOM_B200_MLP_DBG=1 timeout 300 python tools/one_forward.py 2>&1 | grep -E "dbg|ok" | head -80 ) > gpurun_out/mlp_dbg.txt; cat gpurun_out/mlp_dbg.txt
-( timeout 120 tools/bin/umma_probe 2>&1 ) > gpurun_out/umma_probe.txt; cat gpurun_out/umma_probe.txt
+
