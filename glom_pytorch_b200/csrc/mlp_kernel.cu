@@ -343,6 +343,16 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         const float* bsrc = p.b2 + (size_t)t.z * p.d + t.n_blk * BN + part * PART_COLS + (lane & 7) * 4;
         b4k2[0] = __ldg(reinterpret_cast<const float4*>(bsrc));
         b4k2[1] = __ldg(reinterpret_cast<const float4*>(bsrc + 32));
+        // The combine reads this warp's 32 x 64 patch of the fp32 state (streamed to HBM by the previous step) and of C.
+        // Pull those lines into L2 now, ~20 us before the accumulator is complete: the epilogue's dependent global loads
+        // then hit L2 (measured without this: 32 k cycles per K2 tile, as long as its MMAs, and the K1 tiles that follow
+        // in the list stall on the undrained accumulator stage).
+        if (lane < rows_left) {
+          const size_t o = ((size_t)(row0 + lane) * p.L + t.z) * p.d + t.n_blk * BN + part * PART_COLS;
+          prefetch_l2(p.s32_in + o);
+          prefetch_l2(p.s32_in + o + 32);
+          prefetch_l2(p.c_in + o);
+        }
       }
       MLP_TIMED(dw1, mbar_wait(&tfull_bar[as], aphase));
       tc_fence_after_sync();
