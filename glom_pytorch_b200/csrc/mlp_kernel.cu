@@ -109,7 +109,24 @@ __host__ __device__ __forceinline__ MlpTile mlp_decode(const MlpParams& p, int t
   return t;
 }
 
-// next tile index of the cluster's sequence (slot seq % MLP_SLOTS of the ring); -1 = no more work
+// Ring entries are PACKED tile descriptors (decoded once, by the claiming lane: the list position -> tile mapping
+// needs integer divisions, ~100 instructions that 34 warps per pair would otherwise repeat for every tile):
+//   bit 0 kind | bits 1-4 level | bit 5 group within the level (K1) | bits 6-11 n_blk | bits 12-30 m_blk ; -1 = end
+__host__ __device__ __forceinline__ int mlp_pack(const MlpTile& t) {
+  return t.kind | (t.l << 1) | ((t.kind == 0 ? (t.z & 1) : 0) << 5) | (t.n_blk << 6) | (t.m_blk << 12);
+}
+__device__ __forceinline__ MlpTile mlp_unpack(const MlpParams& p, int w) {
+  MlpTile t;
+  t.kind = w & 1;
+  t.l = (w >> 1) & 15;
+  t.n_blk = (w >> 6) & 63;
+  t.m_blk = (w >> 12) & 0x7FFFF;
+  t.z = t.kind ? t.l : 2 * t.l + ((w >> 5) & 1);
+  t.num_kb = t.kind ? ((t.l == p.L - 1) ? 4 * p.d : 8 * p.d) / BK : p.d / BK;
+  return t;
+}
+
+// next tile descriptor of the cluster's sequence (slot seq % MLP_SLOTS of the ring); -1 = no more work
 __device__ __forceinline__ int mlp_fetch(uint64_t* sfull, const volatile int* stile, uint32_t sempty_leader, uint32_t seq) {
   const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
   // plain (cta-scope) wait in both CTAs: the leader's slot is written by a thread of the same CTA, the peer's by
@@ -192,7 +209,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       for (uint32_t seq = 0;; ++seq) {
         const int tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq);
         if (tile < 0) break;
-        const MlpTile t = mlp_decode(p, tile);
+        const MlpTile t = mlp_unpack(p, tile);
         MLP_TIMED(dw0, mbar_wait(&pub_bar[as], aphase));
         if (t.kind == 0) MLP_TIMED(dw1, red_release_gpu_add(p.ready + t.l * p.num_m + t.m_blk, 1));
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -208,7 +225,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       uint32_t pub_seq = 0;
       auto claim = [&]() -> int {
         int tile = atomicAdd(p.counter, 1);
-        if (tile >= p.num_tiles) tile = -1;
+        tile = tile >= p.num_tiles ? -1 : mlp_pack(mlp_decode(p, tile));
         const uint32_t slot = pub_seq % MLP_SLOTS, ph = (pub_seq / MLP_SLOTS) & 1u;
         mbar_wait(&sempty_bar[slot], ph ^ 1u);                  // all 36 readers of the slot's previous use are done
         *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
@@ -227,7 +244,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         else MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
         if (tile < 0) break;
         next_tile = -2;
-        const MlpTile t = mlp_decode(p, tile);
+        const MlpTile t = mlp_unpack(p, tile);
         const CUtensorMap* amap;
         int a_col = 0, b_row;
         const CUtensorMap* bmap;
@@ -294,7 +311,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         int tile;
         MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
         if (tile < 0) break;
-        const MlpTile t = mlp_decode(p, tile);
+        const MlpTile t = mlp_unpack(p, tile);
         MLP_TIMED(dw1, mbar_wait(&tempty_bar[as], aphase ^ 1));      // both CTAs' epilogues drained this accumulator stage
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -324,13 +341,14 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
     const int part = warp >> 2;                // 64-column part of the tile
     uint8_t* patch = patches + (size_t)warp * MLP_PATCH_BYTES;
     float* bias_w = reinterpret_cast<float*>(patch + 2048);      // K1: this warp's 64 bias values (upper patch half)
+    const uint64_t pol_last = l2_policy_evict_last();            // H stays in L2 until this launch's GEMM2 tiles read it
     int as = 0; uint32_t aphase = 0;
     for (uint32_t seq = 0;; ++seq) {
       int tile = 0;
       if (lane == 0) MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
       tile = __shfl_sync(0xffffffffu, tile, 0);
       if (tile < 0) break;
-      const MlpTile t = mlp_decode(p, tile);
+      const MlpTile t = mlp_unpack(p, tile);
       const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
       const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
       // bias of this warp's columns: fetched before the accumulator wait, so the L2 latency overlaps the MMAs
@@ -367,12 +385,12 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
-          if (rows_left >= 32) k1_chunk<true, false>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, 32);
-          else k1_chunk<false, false>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, rows_left);
+          if (rows_left >= 32) k1_chunk<true, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, 32, pol_last);
+          else k1_chunk<false, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, rows_left, pol_last);
         }
       } else {
         K2Chunk kc;
-        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0; kc.prow0 = row0 % p.n;
         kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
         kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
         float rowsq[8];
@@ -428,7 +446,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
 // =====================================================================================
 // Host side
 // =====================================================================================
-bool mlp_fused_supported(const Geometry& g) { return g.d % 256 == 0 && g.L <= MLP_MAX_LEVELS && g.L >= 2; }
+bool mlp_fused_supported(const Geometry& g) {     // limits of the packed tile descriptor: 16 levels, 64 column tiles, 2^19 row blocks
+  return g.d % 256 == 0 && g.d <= 4096 && g.L <= MLP_MAX_LEVELS && g.L >= 2 && (g.rows + 255) / 256 < (1 << 19);
+}
 
 size_t mlp_sched_ints(const Geometry& g) {                       // per launch: tile counter + ready[L * num_m], padded
   const size_t n = 1 + (size_t)g.L * ((g.rows + 255) / 256);

@@ -215,6 +215,16 @@ __device__ __forceinline__ void tma_load_2d_2sm_hint(void* dst, const CUtensorMa
       "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_global_v4_hint(void* p, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

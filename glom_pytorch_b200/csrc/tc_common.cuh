@@ -28,9 +28,13 @@ __device__ __forceinline__ float row_chunk_sumsq(float a, float b, float c, floa
 // ---- K1 epilogue chunk: 32 rows x 32 columns.  Row-per-thread bias + exact-erf GELU + bf16 pack, transpose
 // through the warp's 2 KB patch (16-byte chunk c of row r stored at chunk c ^ ((r >> 1) & 3)), then 64-byte
 // row segments out (8 rows x 64 B per store instruction).
-template <bool FULL, bool STREAM = true>
+// HPOL: 0 = streaming stores (two-kernel step: H is consumed by the NEXT launch, keep it out of L2's way),
+//       1 = L2 evict-last policy `pol` (merged MLP kernel: H is consumed ~10 us later by GEMM2 tiles of the same launch
+//           and must survive the rest of the traffic until then; the consumer's evict-first loads demote it again)
+template <bool FULL, int HPOL = 0>
 __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch,
-                                         __nv_bfloat16* hdst /* &H[row0][col] */, size_t pitch, int lane, int rows_left) {
+                                         __nv_bfloat16* hdst /* &H[row0][col] */, size_t pitch, int lane, int rows_left,
+                                         uint64_t pol = 0) {
   float4 b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) b[i] = *reinterpret_cast<const float4*>(bias + 4 * i);
@@ -52,10 +56,9 @@ __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* b
     const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
     // streaming (evict-first) stores: H (369 MB per step) never fits L2, and letting it through the normal policy
     // evicts the state shadows and weights the GEMMs and the consensus kernel re-read (measured: K1 -4 %)
-    // (the merged MLP kernel keeps H in L2 for its own GEMM2 tiles instead: STREAM = false, default write-back policy)
     if (FULL || r < rows_left) {
-      if (STREAM) __stcs(reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8), val);
-      else *reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8) = val;
+      if (HPOL == 0) __stcs(reinterpret_cast<uint4*>(hdst + (size_t)r * pitch + c * 8), val);
+      else st_global_v4_hint(hdst + (size_t)r * pitch + c * 8, val, pol);
     }
   }
   __syncwarp();
@@ -66,6 +69,7 @@ __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* b
 // that each lane then owns 4 consecutive columns of 8 rows and every global access covers whole 128-byte lines.
 struct K2Chunk {
   int l, L, d, n, row0;
+  int prow0;            // row0 % n: patch index of the band's first row (position table row), computed once per tile
   const float* s32_in; const __nv_bfloat16* c_in; const float* pos;
   float* s32_out; __nv_bfloat16* sb_out; __nv_bfloat16* sp_out;
 };
@@ -94,7 +98,11 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float4 b
       if (FULL || r < rows_left) {
         sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
         cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld));
-        if (has_td) pp[j] = __ldg(reinterpret_cast<const float4*>(k.pos + (size_t)((k.row0 + r) % k.n) * k.d + col + c * 4));
+        if (has_td) {
+          int pr = k.prow0 + r;                       // (row0 + r) % n without a division per row (r < 32)
+          if (k.n >= 32) { if (pr >= k.n) pr -= k.n; } else pr %= k.n;
+          pp[j] = __ldg(reinterpret_cast<const float4*>(k.pos + (size_t)pr * k.d + col + c * 4));
+        }
       }
     }
 #pragma unroll
