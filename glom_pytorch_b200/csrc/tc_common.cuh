@@ -35,14 +35,14 @@ template <bool FULL, int HPOL = 0>
 __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch,
                                          __nv_bfloat16* hdst /* &H[row0][col] */, size_t pitch, int lane, int rows_left,
                                          uint64_t pol = 0) {
-  float4 b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = *reinterpret_cast<const float4*>(bias + 4 * i);
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    pk[2 * i] = gelu_pair_bf16(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), b[i].x, b[i].y);
-    pk[2 * i + 1] = gelu_pair_bf16(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b[i].z, b[i].w);
+    // bias slice read per use (broadcast LDS.128): 32 fewer live registers, so the polynomial's constant pairs stay in
+    // registers instead of being re-materialised for every pair
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * i);
+    pk[2 * i] = gelu_pair_bf16(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), b.x, b.y);
+    pk[2 * i + 1] = gelu_pair_bf16(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b.z, b.w);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c)
