@@ -64,6 +64,8 @@ struct MlpParams {
   int* counter;              // tile counter of this launch (zeroed by the caller)
   int* ready;                // [L * num_m] K1 arrivals per (level, row block) (zeroed by the caller)
   unsigned long long* dbg;   // DBG instantiation only: 16 cycle counters per CTA (GLOM_B200_MLP_DBG=1)
+  int h_load_policy;         // L2 hint of the GEMM2 tiles' H loads: 0 = evict-first on the last column tile only, 1 = on all, 2 = none
+  int h_store_policy;        // H stores: 0 = evict-last, 1 = default write-back policy
 };
 
 struct MlpTile {
@@ -279,6 +281,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
         b_row += (int)cta_rank * (BN / 2);
         const int kbg_n = 4 * p.d / BK;
+        // the row block's H is read by all nN2 column tiles: only the last one may mark it evict-first
+        const bool h_first = p.h_load_policy == 1 || (p.h_load_policy == 0 && t.n_blk == p.nN2 - 1);
         const int claim_kb = t.num_kb > MLP_CLAIM_AHEAD_KB ? t.num_kb - MLP_CLAIM_AHEAD_KB : 0;
         for (int kb = 0; kb < t.num_kb; ++kb) {
           if (leader && kb == claim_kb) MLP_TIMED(dw0, next_tile = claim());   // late look-ahead: see the header
@@ -291,7 +295,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
             const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
             const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
             // last use of these lines by this column tile: evict-first keeps them from displacing weights / state
-            tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, pol_first);
+            if (h_first) tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, pol_first);
+            else tma_load_2d_2sm(sa, amap, bar, 0, blk * BM);
           } else {
             tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
           }
@@ -341,7 +346,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
     const int part = warp >> 2;                // 64-column part of the tile
     uint8_t* patch = patches + (size_t)warp * MLP_PATCH_BYTES;
     float* bias_w = reinterpret_cast<float*>(patch + 2048);      // K1: this warp's 64 bias values (upper patch half)
-    const uint64_t pol_last = l2_policy_evict_last();            // H stays in L2 until this launch's GEMM2 tiles read it
+    // H should stay in L2 until this launch's GEMM2 tiles have read it
+    const uint64_t pol_h = p.h_store_policy == 0 ? l2_policy_evict_last() : l2_policy_evict_normal();
     int as = 0; uint32_t aphase = 0;
     for (uint32_t seq = 0;; ++seq) {
       int tile = 0;
@@ -385,8 +391,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
-          if (rows_left >= 32) k1_chunk<true, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, 32, pol_last);
-          else k1_chunk<false, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, rows_left, pol_last);
+          if (rows_left >= 32) k1_chunk<true, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, 32, pol_h);
+          else k1_chunk<false, 1>(v, bias_w + c0, patch, hrow + c0, (size_t)BK, lane, rows_left, pol_h);
         }
       } else {
         K2Chunk kc;
@@ -512,6 +518,9 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
   p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
   p.counter = sched; p.ready = sched + 1;
+  static int hpol = -1;
+  if (hpol < 0) { const char* e = getenv("GLOM_B200_MLP_HPOL"); hpol = e ? atoi(e) : 0; }      // diagnostics: 10 * store + load
+  p.h_load_policy = hpol % 10; p.h_store_policy = hpol / 10;
 
   // GLOM_B200_MLP_DBG=1 (diagnostics): the instrumented instantiation, synchronised and summarised on stderr for the
   // first launches of the process.  Never set in production: it allocates a small device buffer and blocks the stream.

@@ -220,6 +220,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void st_global_v4_hint(void* p, uint4 v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
                "l"(policy)
@@ -310,17 +315,11 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// gelu(x), x = acc + bias, for two neighbouring columns -> bf16x2.  With u = -|x| and e = Phi(u) = 2^p(u):
-//   gelu(x) = relu(x) + u e = x/2 + u (e - 1/2)          (relu(x) = (x - u) / 2: no max, everything stays packed)
-// p = degree-4 fit of log2(0.5 erfc(a / sqrt 2)), a = -u in [0, 6.5], weighted for the gelu error: |gelu error| <= 7.8e-6
-// over all x (bf16 half-ulp of the result: 2e-5 at 0.01, 2.4e-4 at 0.1); leading coefficient > 0 in u, i.e. p -> -inf for
-// large |x|, so no clamp is needed.  13 instructions per pair (2 LOP3, 2 MUFU.EX2, 8 packed fp32x2 ops, 1 pack): the
-// GELU's issue slots are what slows the tensor pipe in the GEMM1 tiles (profiles/r2_epilogue_probe.txt).
+// (r2: a relu-free packed form x/2 + u (e - 1/2) with a degree-4 fit was tried -- 11 instead of 12 instructions per pair,
+// FFMA2 takes -|x| as an operand modifier and the coefficients as immediates either way -- and dropped: an even-degree fit
+// needs a clamp for |x| > 12 (the peaky golden case overflowed), which costs the instruction it saved; a degree-3 fit is
+// off by up to 6 bf16 ulps on small outputs.  profiles/r2_epilogue_probe.txt: the GELU's ALU work is what slows the tensor
+// pipe in the GEMM1 tiles, 80.7 % -> 62.7 % of peak.)
 __device__ __forceinline__ uint32_t gelu_pair_bf16(float acc0, float acc1, float bias0, float bias1) {
   const uint64_t x = f2_add(f2_pack(acc0, acc1), f2_pack(bias0, bias1));
   float x0, x1;
@@ -328,15 +327,17 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16(float acc0, float acc1, float
   const float u0 = __uint_as_float(__float_as_uint(x0) | 0x80000000u);   // -|x|
   const float u1 = __uint_as_float(__float_as_uint(x1) | 0x80000000u);
   const uint64_t u = f2_pack(u0, u1);
-  uint64_t q = f2_fma(f2_pack(0.0038128290325403214f, 0.0038128290325403214f), u,
-                      f2_pack(0.04376726597547531f, 0.04376726597547531f));
-  q = f2_fma(q, u, f2_pack(-0.46861323714256287f, -0.46861323714256287f));
-  q = f2_fma(q, u, f2_pack(1.1469389200210571f, 1.1469389200210571f));
-  q = f2_fma(q, u, f2_pack(-1.0005745887756348f, -1.0005745887756348f));
+  // p(a) with a = -u: odd coefficients change sign
+  uint64_t q = f2_fma(f2_pack(0.00036467931931838393f, 0.00036467931931838393f), u,
+                      f2_pack(0.006363349035382271f, 0.006363349035382271f));
+  q = f2_fma(q, u, f2_pack(0.05013200640678406f, 0.05013200640678406f));
+  q = f2_fma(q, u, f2_pack(-0.4617065489292145f, -0.4617065489292145f));
+  q = f2_fma(q, u, f2_pack(1.150075078010559f, 1.150075078010559f));
+  q = f2_fma(q, u, f2_pack(-1.0001276731491089f, -1.0001276731491089f));
   float q0, q1;
   f2_unpack(q, q0, q1);
-  const uint64_t t = f2_add(f2_pack(ex2_approx(q0), ex2_approx(q1)), f2_pack(-0.5f, -0.5f));
-  const uint64_t g = f2_fma(u, t, f2_mul(x, f2_pack(0.5f, 0.5f)));
+  const uint64_t e = f2_pack(ex2_approx(q0), ex2_approx(q1));
+  const uint64_t g = f2_fma(u, e, f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));   // relu(x) - |x| Phi(-|x|)
   float g0, g1;
   f2_unpack(g, g0, g1);
   return pack_bf16x2(g0, g1);
