@@ -471,6 +471,7 @@ def main():
             dist.barrier(device_ids=[local_rank])
         enqueue_clock_probe(0)
         torch.cuda.synchronize(dev)
+        _native.kernel_clocks(reset=True)        # in-kernel (clock64, %globaltimer) samples of the timed region only
         ev0.record(stream)
         for i in range(args.steps):
             model(dev_imgs[i % NBUF], iters=T)
@@ -479,6 +480,7 @@ def main():
         enqueue_clock_probe(1)
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
+        kernel_clk = _native.kernel_clocks(reset=True)
         # -------- the same K steps again, back to back, with CUDA events around EVERY kernel launch (library hook):
         # per-kernel durations for the roofline.  Kept out of the region above because an event between two kernels
         # disables their programmatic (PDL) overlap and costs ~1 us each: the instrumented pass is a few % slower.
@@ -725,6 +727,14 @@ def main():
                 "kernels": kern}
         roof["whole_step"]["frac_hbm"] = roof["whole_step"]["hbm_gbs_algorithmic"] / peaks["hbm_gbs"]
         if clocks is not None:
+            # the SM clock INSIDE the tensor-core kernels of the un-instrumented timed region (rank 0): cycles and
+            # %globaltimer ns bracketing each kernel's working phase, summed per kernel kind
+            clocks["in_kernel_sm_mhz"] = {k: round(v[0], 1) for k, v in kernel_clk.items()}
+            clocks["in_kernel_ms_per_step"] = {k: v[1] / args.steps for k, v in kernel_clk.items()}
+            clocks["block0_wait_fractions"] = {k: dict(zip(("mma_lane_waits_operands", "mma_lane_waits_accumulator",
+                                                            "tma_lane_waits_slot", "epilogue_warp0_waits_accumulator",
+                                                            "epilogue_warp0_busy"), v[2]))
+                                               for k, v in kernel_clk.items() if any(v[2])}
             clocks["device_sm_mhz_before"] = dev_mhz_min[0]
             clocks["device_sm_mhz_after"] = dev_mhz_min[1]
             clocks["device_sm_mhz_after_instrumented_pass"] = dev_mhz_min[2]

@@ -16,7 +16,7 @@ EXPORTS = (
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
     "glom_b200_backward", "glom_b200_backward_workspace_bytes",
-    "glom_b200_clock_probe", "glom_b200_mlp_schedule", "glom_b200_islands",
+    "glom_b200_clock_probe", "glom_b200_mlp_schedule", "glom_b200_islands", "glom_b200_kernel_clocks",
 )
 PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize", "mlp_fused")
 
@@ -82,6 +82,8 @@ def load():
     lib.glom_b200_islands.restype = i32
     lib.glom_b200_clock_probe.argtypes = [vp, i32, vp]
     lib.glom_b200_clock_probe.restype = i32
+    lib.glom_b200_kernel_clocks.argtypes = [vp, vp, vp, i32, i32]
+    lib.glom_b200_kernel_clocks.restype = i32
     for f in ("glom_b200_packed_weight_bytes", "glom_b200_pack_weights", "glom_b200_workspace_bytes",
               "glom_b200_workspace_offset", "glom_b200_forward", "glom_b200_tokenize"):
         getattr(lib, f).restype = i32
@@ -180,6 +182,15 @@ def backward(cfg, weight_ptrs, tokens_ptr, pos_ptr, states_ptr, grad_out_ptr, gr
 def clock_probe(out_ptr, spin_us, stream):
     """Enqueue the SM clock probe: out_ptr -> 2 x uint64 device words {cycles, ns} (read after a synchronize)."""
     check(load().glom_b200_clock_probe(out_ptr, spin_us, stream))
+
+
+def kernel_clocks(reset=True):
+    """{kind: (SM MHz inside the kernels, in-kernel ms, [wait fractions of block 0: MMA lane on operands, MMA lane on a free
+    accumulator, TMA lane on a free slot, epilogue warp 0 on an accumulator, epilogue warp 0 busy])} since the last reset."""
+    k = len(PROFILE_KINDS)
+    mhz, ms, wf = (ctypes.c_double * k)(), (ctypes.c_double * k)(), (ctypes.c_double * (5 * k))()
+    check(load().glom_b200_kernel_clocks(mhz, ms, wf, k, int(bool(reset))))
+    return {PROFILE_KINDS[i]: (mhz[i], ms[i], [round(wf[5 * i + j], 4) for j in range(5)]) for i in range(k) if ms[i] > 0}
 
 
 def mlp_schedule(cfg, batch, num_sms=148):

@@ -128,6 +128,9 @@ cudaError_t launch_islands(const float* states, int slabs, int side_h, int side_
                            cudaStream_t st, int* launches);
 
 cudaError_t launch_clock_probe(unsigned long long* out, unsigned long long spin_ns, cudaStream_t st);
+// (cycles, ns) sampled INSIDE the tensor-core kernels since the last reset, by ProfKind (tc_kernels.cu) / merged MLP kernel
+cudaError_t tc_kernel_clocks(unsigned long long* out /* [PROF_KINDS][8] */, bool reset);
+cudaError_t mlp_kernel_clocks(unsigned long long* out /* [2] */, bool reset);
 
 // bf16 tokeniser: patchify + cast (CUDA cores), then the tcgen05 GEMM
 cudaError_t launch_patchify_bf16(const float* img, const float* w, __nv_bfloat16* patches, __nv_bfloat16* wtok, int B,

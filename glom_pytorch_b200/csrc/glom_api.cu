@@ -114,6 +114,15 @@ static int device_info(DeviceInfo* out) {
     g_dev[dev].ok = (major == 10);
     g_dev[dev].sms = sms;
     g_dev_known[dev] = true;
+    // GLOM_B200_L2_PERSIST_MB (diagnostics): set-aside for L2 lines written / read with an evict-last policy
+    if (const char* pe = getenv("GLOM_B200_L2_PERSIST_MB")) {
+      int maxp = 0;
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      size_t want = (size_t)atoi(pe) << 20;
+      if (want > (size_t)maxp) want = (size_t)maxp;
+      const cudaError_t pe_rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      fprintf(stderr, "[glom_b200] persisting L2 set-aside: asked %zu MB of max %d MB -> %s\n", want >> 20, maxp >> 20, cudaGetErrorString(pe_rc));
+    }
   }
   if (!g_encode) {
     void* fn = nullptr;
@@ -224,10 +233,12 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
     cudaError_t e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
     if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "prep launch: %s", cudaGetErrorString(e));
-    // merged MLP kernel (dim % 256 == 0): its tile / dependency counters for every step, zeroed once per call.
-    // GLOM_B200_SPLIT_MLP=1 (diagnostics, A/B timing) keeps the three-kernel step.
-    const char* split_env = getenv("GLOM_B200_SPLIT_MLP");       // read per call: tests toggle it in-process
-    const bool split_mlp = split_env && split_env[0] == '1';
+    // The step is three launches (GEMM1+GELU, consensus, GEMM2+combine).  GLOM_B200_MERGED_MLP=1 (A/B experiment, kept
+    // bit-identical and tested) replaces the two GEMM launches by the merged persistent MLP kernel (dim % 256 == 0): its
+    // list heads / dependency counters for every step are zeroed once per call.  Measured slower on B200 (profiles/README.md,
+    // r2: H does not survive in L2 between its GEMM1 and GEMM2 tiles), hence opt-in.
+    const char* merged_env = getenv("GLOM_B200_MERGED_MLP");     // read per call: tests toggle it in-process
+    const bool split_mlp = !(merged_env && merged_env[0] == '1');
     int* sched = nullptr;
     if (wl.sched_bytes && !split_mlp && iters > 0) {
       sched = reinterpret_cast<int*>(ws + wl.sched_off);
@@ -396,6 +407,26 @@ GLOM_B200_API int glom_b200_clock_probe(uint64_t* out_cycles_ns, int spin_us, vo
   cudaError_t e = launch_clock_probe(reinterpret_cast<unsigned long long*>(out_cycles_ns), (unsigned long long)spin_us * 1000ull,
                                      static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "clock probe launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_kernel_clocks(double* mhz_by_kind, double* ms_by_kind, double* wait_frac, int kinds, int reset) {
+  if (!mhz_by_kind || !ms_by_kind || kinds < 1) return fail(GLOM_B200_ERR_INVALID, "kernel clocks: bad arguments");
+  unsigned long long acc[PROF_KINDS][8];
+  unsigned long long mlp[2];
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = tc_kernel_clocks(&acc[0][0], reset != 0);
+  if (e == cudaSuccess) e = mlp_kernel_clocks(mlp, reset != 0);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "kernel clocks: %s", cudaGetErrorString(e));
+  for (int j = 0; j < 8; ++j) acc[PROF_MLP][j] = 0;
+  acc[PROF_MLP][0] = mlp[0]; acc[PROF_MLP][1] = mlp[1];
+  for (int i = 0; i < kinds; ++i) {
+    const bool have = i < PROF_KINDS && acc[i][1] > 0;
+    mhz_by_kind[i] = have ? 1e3 * (double)acc[i][0] / (double)acc[i][1] : 0.0;     // cycles per ns -> MHz
+    ms_by_kind[i] = have ? 1e-6 * (double)acc[i][1] : 0.0;
+    if (wait_frac)
+      for (int j = 0; j < 5; ++j) wait_frac[5 * i + j] = have && acc[i][0] ? (double)acc[i][2 + j] / (double)acc[i][0] : 0.0;
+  }
   return 0;
 }
 

@@ -6,20 +6,25 @@
 //   as 256 x 256 CTA-pair tiles (tcgen05 cta_group::2, the machinery of gemm_kernel in tc_kernels.cu) drawn from ONE
 //   ordered work list by a dynamic scheduler, with per-(level, row block) dependency counters in global memory:
 //
-//   * Work list: level-major (top level last: its GEMM2 tiles cost half, which keeps the tail short); inside a
-//     level the K1 tiles of row block m (256 rows: both MLP groups, all 4d/256 column tiles) are followed by the K2
-//     tiles of row block m - delay.  Every K2 tile therefore depends only on tiles EARLIER in the list, so handing the
-//     list out in order can never deadlock, and by the time a K2 tile is drawn its producers (>= one full wave of
-//     clusters earlier) have normally retired: the hidden activations H are consumed ~10 us after they were written,
-//     while they are still in L2.  The 2 x 369 MB HBM round trip of H of the two-kernel path (K1 launch, then K2
-//     launch) becomes L2 traffic; only the eventual write-back of the dead lines remains.
-//   * Scheduler: the leader CTA's TMA producer lane draws the next tile index with atomicAdd while it issues the last
-//     loads of the current tile (a claimed tile starts loading ~1-2 us later; claiming further ahead was measured to
-//     wreck the dependency order: a cluster busy with a 20 us K2 tile sat on K1 tiles other clusters waited for) and
-//     publishes it through an 8-slot shared-memory ring to the MMA / epilogue / publisher roles of BOTH CTAs of the pair
-//     and to the peer's TMA lane (local store + mbarrier for its own CTA, st.async + complete_tx for the peer).
-//     Tiles of very different cost (K = d for K1, 8d for K2, 4d for the top level) balance themselves; there is no
-//     static-schedule quantisation.
+//   * Work lists: two ordered lists, both level-major (top level last: its GEMM2 tiles cost half, which keeps the
+//     tail short) and then by 256-row block: the K1 list (per row block: both MLP groups x 4d/256 column tiles) and the
+//     K2 list (per row block: d/256 column tiles).  A K2 tile depends on the K1 tiles of its (level, row block).
+//   * Scheduler (adaptive cluster roles): the leader CTA's TMA producer lane draws the next tile while it issues the last
+//     loads of the current one.  It looks at the heads of both lists: `lag` = row blocks between the K1 head and the K2
+//     head.  If the lag has reached a threshold and the K2 head's dependencies are complete, it takes the K2 head
+//     (compare-and-swap on the K2 counter), else the next K1 tile (atomicAdd); once the K1 list is exhausted everybody
+//     takes K2 tiles in order (their dependencies are claimed, running, and never wait themselves: no deadlock).  The
+//     threshold is lower for a cluster whose previous tile was a K2 tile, so clusters keep their role for long stretches
+//     while the NUMBER of clusters on each kind adapts to the two kinds' actual rates.  Why roles: a K2 tile's MMAs take
+//     8x a K1 tile's and its epilogue (fp32 state in / out, C, two shadows: ~20 k cycles) as long as five K1 tiles; with
+//     two TMEM accumulator stages a K1 tile scheduled behind a K2 tile waits for that epilogue to drain (measured with
+//     the mixed in-order list of r2a: MMA lane 22 % waiting for a free accumulator).  A cluster that stays on K2 tiles
+//     hides each epilogue behind the next tile's 32 k cycles of MMAs; one that stays on K1 tiles alternates stages
+//     every ~4-7 k cycles.  H is consumed a few row blocks (~10 us) after it was written, while still in L2: the
+//     2 x 369 MB HBM round trip of the two-kernel path becomes L2 traffic plus the eventual write-back.
+//     The drawn tile is published through an 8-slot shared-memory ring to the MMA / epilogue / publisher roles of BOTH
+//     CTAs of the pair and to the peer's TMA lane (local store + mbarrier for its own CTA, st.async + complete_tx for
+//     the peer).
 //   * Dependencies: the 16 epilogue warps of a CTA arrive on a shared-memory mbarrier once their stores of a tile are
 //     issued; one publisher lane per CTA turns that into ONE gpu-scope release (red.release.gpu.add on
 //     ready[level][row block]) per CTA and K1 tile, off the epilogue warps' critical path (cumulativity: stores ->
@@ -44,24 +49,26 @@ constexpr uint32_t MLP_PATCH_BYTES = 4096;        // per-warp transpose patch (K
 constexpr uint32_t MLP_TMEM_COLS = 2 * MLP_BN;    // two accumulator stages
 constexpr size_t MLP_SMEM_BYTES = 1024 + (size_t)MLP_STAGES * MLP_STAGE_BYTES + (size_t)MLP_EPI_WARPS * MLP_PATCH_BYTES + 512;
 constexpr int MLP_SEMPTY_COUNT = (MLP_EPI_WARPS + 2) + (MLP_EPI_WARPS + 2);   // leader: epilogue + MMA + publisher; peer: epilogue + TMA + publisher
-constexpr int MLP_CLAIM_AHEAD_KB = 4;             // the next tile is claimed this many k-blocks before the current tile's last load
 constexpr int MLP_MAX_LEVELS = 16;
+
+__device__ unsigned long long g_mlp_clk[2];     // in-kernel clock sample (cycles, ns), see clock_sample_begin
 
 struct MlpParams {
   int rows, d, L, n;
   int num_m;                 // 256-row pair tiles
   int nN1, nN2;              // column tiles of GEMM1 (4d / 256) and GEMM2 (d / 256)
   int m128;                  // 128-row blocks of the (padded) hidden buffer H
-  int delay;                 // row blocks between the K1 tiles of a row block and its K2 tiles
-  int num_tiles;
-  int level_base[MLP_MAX_LEVELS + 1];   // first list index of level l
+  int n1_tiles, n2_tiles;    // lengths of the K1 / K2 lists
+  int lvl1_base[MLP_MAX_LEVELS + 1];    // first K1-list index of level l (the top level has one group, the others two)
+  int lag_hi, lag_lo;        // row blocks the K1 head must lead the K2 head by before a cluster takes the K2 head:
+                             // lag_hi after a K1 tile, lag_lo after a K2 tile (sticky roles)
   const float* b1;           // (G * 4d)
   const float* b2;           // (L * d)   b2bu + b2td
   __nv_bfloat16* h;
   const float* s32_in;  const __nv_bfloat16* c_in;  const float* pos;
   float* s32_out;  __nv_bfloat16* sb_out;  __nv_bfloat16* sp_out;  float* nsq_out;
   int nparts;
-  int* counter;              // tile counter of this launch (zeroed by the caller)
+  int* counter;              // [2] heads of the K1 and K2 lists of this launch (zeroed by the caller)
   int* ready;                // [L * num_m] K1 arrivals per (level, row block) (zeroed by the caller)
   unsigned long long* dbg;   // DBG instantiation only: 16 cycle counters per CTA (GLOM_B200_MLP_DBG=1)
   int h_load_policy;         // L2 hint of the GEMM2 tiles' H loads: 0 = evict-first on the last column tile only, 1 = on all, 2 = none
@@ -74,40 +81,24 @@ struct MlpTile {
   int l, m_blk, n_blk, num_kb;
 };
 
-__host__ __device__ __forceinline__ MlpTile mlp_decode(const MlpParams& p, int tile) {
+// i-th tile of the K1 list / j-th tile of the K2 list
+__host__ __device__ __forceinline__ MlpTile mlp_decode1(const MlpParams& p, int i) {
   int l = 0;
-  while (l + 1 < p.L && tile >= p.level_base[l + 1]) ++l;
-  const int idx = tile - p.level_base[l];
-  const int ng = (l == p.L - 1) ? 1 : 2;                // the top level has no top-down group (:137)
-  const int c1 = ng * p.nN1, c2 = p.nN2;
-  const int dl = p.delay < p.num_m ? p.delay : p.num_m;
-  int m, r;
-  bool k2;
-  if (idx < dl * c1) {                                  // head: the first `delay` row blocks have no K2 tiles behind them yet
-    m = idx / c1; r = idx - m * c1; k2 = false;
-  } else {
-    int j = idx - dl * c1;
-    const int per = c1 + c2, zone = (p.num_m - dl) * per;
-    if (j < zone) {                                     // steady state: K1 tiles of row block dl + q, then K2 tiles of q
-      const int q = j / per;
-      r = j - q * per;
-      if (r < c1) { m = dl + q; k2 = false; } else { m = q; r -= c1; k2 = true; }
-    } else {                                            // tail: K2 tiles of the last `delay` row blocks
-      j -= zone;
-      const int q = j / c2;
-      m = p.num_m - dl + q; r = j - q * c2; k2 = true;
-    }
-  }
+  while (l + 1 < p.L && i >= p.lvl1_base[l + 1]) ++l;
+  const int idx = i - p.lvl1_base[l];
+  const int c1 = ((l == p.L - 1) ? 1 : 2) * p.nN1;      // the top level has no top-down group (:137)
+  const int m = idx / c1, r = idx - m * c1;
+  const int gi = r / p.nN1;
   MlpTile t;
-  t.l = l; t.m_blk = m;
-  if (k2) {
-    t.kind = 1; t.z = l; t.n_blk = r;
-    t.num_kb = ((l == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;
-  } else {
-    const int gi = r / p.nN1;
-    t.kind = 0; t.z = 2 * l + gi; t.n_blk = r - gi * p.nN1;
-    t.num_kb = p.d / BK;
-  }
+  t.kind = 0; t.l = l; t.m_blk = m; t.z = 2 * l + gi; t.n_blk = r - gi * p.nN1; t.num_kb = p.d / BK;
+  return t;
+}
+__host__ __device__ __forceinline__ MlpTile mlp_decode2(const MlpParams& p, int j) {
+  const int per = p.num_m * p.nN2;
+  const int l = j / per, r = j - l * per;
+  MlpTile t;
+  t.kind = 1; t.l = l; t.z = l; t.m_blk = r / p.nN2; t.n_blk = r - t.m_blk * p.nN2;
+  t.num_kb = ((l == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;
   return t;
 }
 
@@ -137,6 +128,16 @@ __device__ __forceinline__ int mlp_fetch(uint64_t* sfull, const volatile int* st
   const int tile = stile[slot];
   // the release of the slot must not overtake the read above: make the arrive depend on the value
   if (tile >= -1) mbar_arrive_cluster(sempty_leader + 8u * slot);
+  return tile;
+}
+// the same for a converged warp (control warps, see elect_one): every lane waits and reads, the elected lane releases
+__device__ __forceinline__ int mlp_fetch_warp(uint64_t* sfull, const volatile int* stile, uint32_t sempty_leader, uint32_t seq,
+                                              uint32_t elected) {
+  const uint32_t slot = seq % MLP_SLOTS, ph = (seq / MLP_SLOTS) & 1u;
+  mbar_wait(&sfull[slot], ph);
+  const int tile = stile[slot];
+  __syncwarp();                                    // every lane has read the slot before it is handed back
+  if (elected && tile >= -1) mbar_arrive_cluster(sempty_leader + 8u * slot);
   return tile;
 }
 
@@ -196,6 +197,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();                  // global memory (counters included) is touched only after the previous kernel finished
+  const bool clk_thread = blockIdx.x == 0 && warp == W_ALLOC && lane == 0;
+  ClockSample clk_s{};
+  if (clk_thread) clk_s = clock_sample_begin();
 
   const uint32_t sempty_leader = mapa_shared(smem_u32(&sempty_bar[0]), 0);
   const long long k_t0 = DBG ? clock64() : 0;
@@ -220,46 +224,97 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
     }
   } else if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint64_t pol_first = l2_policy_evict_first();
-      // leader: draws the tile index and publishes it to the ring (both CTAs); peer: reads the ring like everyone else
-      uint32_t pub_seq = 0;
-      auto claim = [&]() -> int {
-        int tile = atomicAdd(p.counter, 1);
-        tile = tile >= p.num_tiles ? -1 : mlp_pack(mlp_decode(p, tile));
-        const uint32_t slot = pub_seq % MLP_SLOTS, ph = (pub_seq / MLP_SLOTS) & 1u;
-        mbar_wait(&sempty_bar[slot], ph ^ 1u);                  // all 36 readers of the slot's previous use are done
-        *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
-        mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
-        const uint32_t rbar = mapa_shared(smem_u32(&sfull_bar[slot]), 1);
-        mbar_arrive_expect_tx_cluster(rbar, 4);                               // peer CTA: value + completion in one
-        st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
-        ++pub_seq;
-        return tile;
-      };
-      int next_tile = -2;
-      if (leader) MLP_TIMED(dw0, next_tile = claim());
-      for (uint32_t seq = 0;; ++seq) {
-        int tile;
-        if (leader) tile = next_tile;
-        else MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
-        if (tile < 0) break;
-        next_tile = -2;
-        const MlpTile t = mlp_unpack(p, tile);
-        const CUtensorMap* amap;
-        int a_col = 0, b_row;
-        const CUtensorMap* bmap;
-        if (t.kind == 0) {
-          const int l = t.l;
-          if (t.z == 0) { amap = &map_x; a_col = 0; }                          // bottom-up level 0 reads the tokens (:132)
-          else if (t.z & 1) { amap = &map_sp; a_col = l * p.d; }               // top-down l reads S[l+1]+pos (:136)
-          else { amap = &map_sb; a_col = (l - 1) * p.d; }                      // bottom-up l reads S[l-1]   (:134)
-          bmap = &map_w1;
-          b_row = t.z * 4 * p.d + t.n_blk * BN;
-        } else {
-          amap = &map_h; bmap = &map_w2;
-          b_row = t.z * p.d + t.n_blk * BN;
+    // warp-converged (see elect_one): all lanes walk the tile sequence and poll the ring barriers, the elected lane
+    // claims tiles, waits for dependencies and issues the loads
+    const uint32_t elected = elect_one();
+    const int elected_lane = __ffs(__ballot_sync(0xffffffffu, elected != 0)) - 1;
+    int stage = 0; uint32_t phase = 0;
+    const uint64_t pol_first = l2_policy_evict_first();
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t bar0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    const int kbg_n = 4 * p.d / BK;
+    const int blk_skip = (p.m128 - 1) * kbg_n;
+    // leader: draws the tile index and publishes it to the ring (both CTAs); peer: reads the ring like everyone else
+    uint32_t pub_seq = 0;
+    int last_kind = 0;
+    // The draw is a chain of dependent L2 round trips (list heads -> dependency counter -> compare-and-swap / add, ~1.5 k
+    // cycles).  Done in one piece between two loads it starves the MMA pipe (measured: MMA lane 59 % waiting for
+    // operands); it is therefore split into four phases issued two k-blocks apart, so each phase's result has arrived
+    // when the next one needs it and the TMA issue stream never waits on it.
+    int c_i1 = 0, c_j = 0, c_ready = 0, c_res = 0, c_mode = 0;      // c_mode: 0 = K1 add pending, 1 = K2 cas pending
+    auto claim_a = [&]() {                          // list heads (approximate: others move them)
+      c_i1 = *reinterpret_cast<volatile int*>(p.counter);
+      c_j = *reinterpret_cast<volatile int*>(p.counter + 1);
+    };
+    auto claim_b = [&]() {                          // lag reached? -> look at the K2 head's dependency counter
+      c_mode = 0;
+      if (c_i1 < p.n1_tiles && c_j < p.n2_tiles) {
+        const MlpTile h1 = mlp_decode1(p, c_i1), h2 = mlp_decode2(p, c_j);
+        const int lag = (h1.l - h2.l) * p.num_m + (h1.m_blk - h2.m_blk);
+        if (lag >= (last_kind ? p.lag_lo : p.lag_hi)) {
+          c_mode = 1;
+          c_ready = ld_acquire_gpu(p.ready + h2.l * p.num_m + h2.m_blk);
+        }
+      }
+    };
+    auto claim_c = [&]() {                          // take the K2 head (its producers have retired) or the next K1 tile
+      if (c_mode == 1) {
+        const int l2 = c_j / (p.num_m * p.nN2);
+        if (c_ready >= ((l2 == p.L - 1) ? 1 : 2) * p.nN1 * 2) { c_res = atomicCAS(p.counter + 1, c_j, c_j + 1); return; }
+        c_mode = 0;
+      }
+      c_res = atomicAdd(p.counter, 1);
+    };
+    auto claim_d = [&]() -> int {                   // resolve and publish to the ring of both CTAs
+      int tile;
+      if (c_mode == 1 && c_res == c_j) tile = mlp_pack(mlp_decode2(p, c_j));
+      else {
+        const int i = c_mode == 1 ? atomicAdd(p.counter, 1) : c_res;       // lost the race for the K2 head: a K1 tile
+        if (i < p.n1_tiles) tile = mlp_pack(mlp_decode1(p, i));
+        else {                                      // K1 list exhausted: K2 tiles in order (the TMA lane waits for their producers)
+          const int j = atomicAdd(p.counter + 1, 1);
+          tile = j < p.n2_tiles ? mlp_pack(mlp_decode2(p, j)) : -1;
+        }
+      }
+      if (DBG && tile >= 0) { if (tile & 1) { ++dw4; if (!last_kind) dw4 += 1ull << 32; } }
+      last_kind = tile >= 0 ? (tile & 1) : 0;
+      const uint32_t slot = pub_seq % MLP_SLOTS, ph = (pub_seq / MLP_SLOTS) & 1u;
+      mbar_wait(&sempty_bar[slot], ph ^ 1u);                  // all 36 readers of the slot's previous use are done
+      *reinterpret_cast<volatile int*>(&stile[slot]) = tile;
+      mbar_arrive(&sfull_bar[slot]);                                        // own CTA (release.cta)
+      const uint32_t rbar = mapa_shared(smem_u32(&sfull_bar[slot]), 1);
+      mbar_arrive_expect_tx_cluster(rbar, 4);                               // peer CTA: value + completion in one
+      st_async_b32(mapa_shared(smem_u32(&stile[slot]), 1), (uint32_t)tile, rbar);
+      ++pub_seq;
+      return tile;
+    };
+    auto claim = [&]() -> int { claim_a(); claim_b(); claim_c(); return claim_d(); };     // first tile: nothing to overlap with
+    int next_tile = -2;
+    if (leader) {
+      if (elected) MLP_TIMED(dw0, next_tile = claim());
+      next_tile = __shfl_sync(0xffffffffu, next_tile, elected_lane);
+    }
+    for (uint32_t seq = 0;; ++seq) {
+      int tile;
+      if (leader) tile = next_tile;
+      else MLP_TIMED(dw0, tile = mlp_fetch_warp(sfull_bar, stile, sempty_leader, seq, elected));
+      if (tile < 0) break;
+      next_tile = -2;
+      const MlpTile t = mlp_unpack(p, tile);
+      const CUtensorMap* amap;
+      int a_col = 0, b_row;
+      const CUtensorMap* bmap;
+      if (t.kind == 0) {
+        const int l = t.l;
+        if (t.z == 0) { amap = &map_x; a_col = 0; }                          // bottom-up level 0 reads the tokens (:132)
+        else if (t.z & 1) { amap = &map_sp; a_col = l * p.d; }               // top-down l reads S[l+1]+pos (:136)
+        else { amap = &map_sb; a_col = (l - 1) * p.d; }                      // bottom-up l reads S[l-1]   (:134)
+        bmap = &map_w1;
+        b_row = t.z * 4 * p.d + t.n_blk * BN;
+      } else {
+        amap = &map_h; bmap = &map_w2;
+        b_row = t.z * p.d + t.n_blk * BN;
+        if (elected) {
           // all K1 tiles of this (level, row block) have published their part of H
           const int need = ((t.l == p.L - 1) ? 1 : 2) * p.nN1 * 2;              // one arrival per CTA and K1 tile
           const int* ctr = p.ready + t.l * p.num_m + t.m_blk;
@@ -278,43 +333,63 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
           }
           fence_proxy_async_global();          // generic-proxy stores of H (other SMs) -> this thread's TMA loads
         }
-        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
-        b_row += (int)cta_rank * (BN / 2);
-        const int kbg_n = 4 * p.d / BK;
-        // the row block's H is read by all nN2 column tiles: only the last one may mark it evict-first
-        const bool h_first = p.h_load_policy == 1 || (p.h_load_policy == 0 && t.n_blk == p.nN2 - 1);
-        const int claim_kb = t.num_kb > MLP_CLAIM_AHEAD_KB ? t.num_kb - MLP_CLAIM_AHEAD_KB : 0;
-        for (int kb = 0; kb < t.num_kb; ++kb) {
-          if (leader && kb == claim_kb) MLP_TIMED(dw0, next_tile = claim());   // late look-ahead: see the header
-          MLP_TIMED(dw2, mbar_wait(&empty_bar[stage], phase ^ 1));
-          uint8_t* sa = smem + (size_t)stage * MLP_STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * MLP_STAGE_BYTES);   // both CTAs' bytes land here
-          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          if (t.kind == 1) {
-            // block (group g, 128-row block, 64-wide k block): [H_bu,l | H_td,l] are groups 2l and 2l+1
-            const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
-            const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
-            // last use of these lines by this column tile: evict-first keeps them from displacing weights / state
-            if (h_first) tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, pol_first);
-            else tma_load_2d_2sm(sa, amap, bar, 0, blk * BM);
-          } else {
-            tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
-          }
-          tma_load_2d_2sm(sa + A_STAGE_BYTES, bmap, bar, kb * BK, b_row);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+        __syncwarp();
       }
-      if (DBG) { dbg[2] = dw0; dbg[3] = dw1; dbg[4] = dw2; dbg[15] = dw3; }
+      const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
+      b_row += (int)cta_rank * (BN / 2);
+      // K2: block (group g, 128-row block, 64-wide k block); [H_bu,l | H_td,l] are groups 2l and 2l+1
+      const int blk0 = (2 * t.z * p.m128 + (a_row >> 7)) * kbg_n;
+      // the row block's H is read by all nN2 column tiles: only the last one may mark it evict-first
+      const bool h_first = p.h_load_policy == 1 || (p.h_load_policy == 0 && t.n_blk == p.nN2 - 1);
+      // claim phases at k-blocks ca, ca + 1, ca + 2, ca + 3 (late look-ahead: a claimed tile starts loading
+      // ~1-2 us later; claiming further ahead lets a cluster busy with a long tile sit on tiles others wait for)
+      // (the draw is published 4 k-blocks before the tile's last load: the peer CTA's TMA lane learns about the next
+      // tile through the ring and must not start it late)
+      const int cs = 1;
+      const int ca = t.num_kb >= 7 ? t.num_kb - 7 : 0;
+      for (int kb = 0; kb < t.num_kb; ++kb) {
+        if (leader) {
+          if (elected) {
+            if (kb == ca) MLP_TIMED(dw0, claim_a());
+            else if (kb == ca + cs) MLP_TIMED(dw0, claim_b());
+            else if (kb == ca + 2 * cs) MLP_TIMED(dw0, claim_c());
+            else if (kb == ca + 2 * cs + 1) MLP_TIMED(dw0, next_tile = claim_d());
+          }
+          __syncwarp();
+        }
+        MLP_TIMED(dw2, mbar_wait(&empty_bar[stage], phase ^ 1));
+        if (elected) {
+          const uint32_t sa = smem0 + (uint32_t)stage * MLP_STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * MLP_STAGE_BYTES);   // both CTAs' bytes land here
+          const uint32_t bar = bar0 + 8u * (uint32_t)stage;
+          if (t.kind == 1) {
+            const int blk = blk0 + kb + (kb >= kbg_n ? blk_skip : 0);
+            // last use of these lines by this column tile: evict-first keeps them from displacing weights / state
+            if (h_first) tma_load_2d_2sm_sa_hint(sa, amap, bar, 0, blk * BM, pol_first);
+            else tma_load_2d_2sm_sa(sa, amap, bar, 0, blk * BM);
+          } else {
+            tma_load_2d_2sm_sa(sa, amap, bar, a_col + kb * BK, a_row);
+          }
+          tma_load_2d_2sm_sa(sa + A_STAGE_BYTES, bmap, bar, kb * BK, b_row);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) next_tile = __shfl_sync(0xffffffffu, next_tile, elected_lane);
     }
+    if (DBG && elected) { dbg[2] = dw0; dbg[3] = dw1; dbg[4] = dw2; dbg[15] = dw3; if (leader) dbg[12] = dw4; }
   } else if (warp == W_MMA) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only), warp-converged
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      const uint32_t elected = elect_one();
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (uint32_t seq = 0;; ++seq) {
         int tile;
-        MLP_TIMED(dw0, tile = mlp_fetch(sfull_bar, stile, sempty_leader, seq));
+        MLP_TIMED(dw0, tile = mlp_fetch_warp(sfull_bar, stile, sempty_leader, seq, elected));
         if (tile < 0) break;
         const MlpTile t = mlp_unpack(p, tile);
         MLP_TIMED(dw1, mbar_wait(&tempty_bar[as], aphase ^ 1));      // both CTAs' epilogues drained this accumulator stage
@@ -323,22 +398,23 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         for (int kb = 0; kb < t.num_kb; ++kb) {
           MLP_TIMED(dw2, mbar_wait(&full_bar[stage], phase));
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * MLP_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          if (elected) {
+            const uint64_t ad = a_desc0 + (uint64_t)(stage * (int)(MLP_STAGE_BYTES >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(stage * (int)(MLP_STAGE_BYTES >> 4));
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 1; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
           }
-          umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
+        if (elected) umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (DBG) ++dw3;
       }
-      if (DBG) { dbg[5] = dw0; dbg[6] = dw1; dbg[7] = dw2; dbg[14] = dw3; }
+      if (DBG && elected) { dbg[5] = dw0; dbg[6] = dw1; dbg[7] = dw2; dbg[14] = dw3; }
     }
   } else if (warp < MLP_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (16 warps)
@@ -435,18 +511,28 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
       if (DBG) { if (t.kind == 0) dw2 += (unsigned long long)(clock64() - e_t0); else dw3 += (unsigned long long)(clock64() - e_t0); }
     }
     if (DBG && warp == 0 && lane == 0) {
-      dbg[8] = dw0; dbg[9] = dw1; dbg[10] = dw2; dbg[11] = dw3; dbg[12] = dw4;
+      dbg[8] = dw0; dbg[9] = dw1; dbg[10] = dw2; dbg[11] = dw3;
       dbg[13] = (unsigned long long)(clock64() - k_t0);
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (clk_thread) clock_sample_end(clk_s, g_mlp_clk);
   cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
   if (warp == W_ALLOC) {
     tc_fence_after_sync();
     tmem_dealloc_2sm(tmem_base, MLP_TMEM_COLS);
   }
+}
+
+cudaError_t mlp_kernel_clocks(unsigned long long* out /* [2] */, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_mlp_clk, sizeof(unsigned long long) * 2);
+  if (e == cudaSuccess && reset) {
+    static const unsigned long long zeros[2] = {};
+    e = cudaMemcpyToSymbol(g_mlp_clk, zeros, sizeof(zeros));
+  }
+  return e;
 }
 
 // =====================================================================================
@@ -456,12 +542,12 @@ bool mlp_fused_supported(const Geometry& g) {     // limits of the packed tile d
   return g.d % 256 == 0 && g.d <= 4096 && g.L <= MLP_MAX_LEVELS && g.L >= 2 && (g.rows + 255) / 256 < (1 << 19);
 }
 
-size_t mlp_sched_ints(const Geometry& g) {                       // per launch: tile counter + ready[L * num_m], padded
-  const size_t n = 1 + (size_t)g.L * ((g.rows + 255) / 256);
+size_t mlp_sched_ints(const Geometry& g) {                       // per launch: two list heads + ready[L * num_m], padded
+  const size_t n = 2 + (size_t)g.L * ((g.rows + 255) / 256);
   return (n + 31) / 32 * 32;
 }
 
-// work-list geometry of one launch (everything mlp_decode needs)
+// work-list geometry of one launch (everything mlp_decode1 / mlp_decode2 and the claim policy need)
 static void mlp_list_params(const Geometry& g, int num_sms, MlpParams* pp) {
   MlpParams& p = *pp;
   const int d = g.d, L = g.L, rows = g.rows;
@@ -469,32 +555,39 @@ static void mlp_list_params(const Geometry& g, int num_sms, MlpParams* pp) {
   p.num_m = (rows + 255) / 256;
   p.nN1 = 4 * d / MLP_BN; p.nN2 = d / MLP_BN;
   p.m128 = (rows + BM - 1) / BM;
-  const int max_clusters = num_sms / 2;
-  // K2 tiles trail their row block's K1 tiles by ~3 waves of clusters worth of list entries: a claimed K1 tile retires
-  // (loads, MMAs, epilogue, release) within ~10 us, during which the chip claims ~2.5 waves of tiles
-  const int per_block = 2 * p.nN1 + p.nN2;
-  static int delay_override = -2;
-  if (delay_override == -2) { const char* e = getenv("GLOM_B200_MLP_DELAY"); delay_override = e ? atoi(e) : -1; }
-  p.delay = delay_override >= 0 ? delay_override : (3 * max_clusters + per_block - 1) / per_block;
-  if (p.delay < 1) p.delay = 1;
   int base = 0;
   for (int l = 0; l < L; ++l) {
-    p.level_base[l] = base;
-    base += p.num_m * (((l == L - 1) ? 1 : 2) * p.nN1 + p.nN2);
+    p.lvl1_base[l] = base;
+    base += p.num_m * ((l == L - 1) ? 1 : 2) * p.nN1;
   }
-  p.level_base[L] = base;
-  p.num_tiles = base;
+  p.lvl1_base[L] = base;
+  p.n1_tiles = base;
+  p.n2_tiles = L * p.num_m * p.nN2;
+  // lag thresholds: with every cluster on K1 tiles, num_sms / 2 tiles = that many / (2 nN1) row blocks are in flight; a K2
+  // head that far behind the K1 head has normally retired all its producers
+  const int max_clusters = num_sms / 2;
+  const int inflight = (max_clusters + 2 * p.nN1 - 1) / (2 * p.nN1);
+  static int lag_override = -2, lag_lo_override = -2;
+  if (lag_override == -2) { const char* e = getenv("GLOM_B200_MLP_LAG"); lag_override = e ? atoi(e) : -1; }
+  if (lag_lo_override == -2) { const char* e = getenv("GLOM_B200_MLP_LAG_LO"); lag_lo_override = e ? atoi(e) : -1; }
+  p.lag_hi = lag_override >= 0 ? lag_override : inflight + 3;
+  p.lag_lo = lag_lo_override >= 0 ? lag_lo_override : (p.lag_hi + 1) / 2;
+  if (p.lag_hi < 1) p.lag_hi = 1;
+  if (p.lag_lo < 1) p.lag_lo = 1;
+  if (p.lag_lo > p.lag_hi) p.lag_lo = p.lag_hi;
 }
 
-// diagnostics / host tests: the ordered work list as (kind, z, m_blk, n_blk) quadruples
+// diagnostics / host tests: the two ordered work lists, K1 list first, as (kind, z, m_blk, n_blk) quadruples;
+// *delay = the lag threshold (row blocks) at which a cluster coming from a K1 tile takes the K2 head
 int mlp_schedule_dump(const Geometry& g, int num_sms, int* out, int capacity, int* num_tiles, int* delay) {
   if (!mlp_fused_supported(g)) return -1;
   MlpParams p{};
   mlp_list_params(g, num_sms, &p);
-  if (num_tiles) *num_tiles = p.num_tiles;
-  if (delay) *delay = p.delay;
-  for (int i = 0; i < p.num_tiles && i < capacity; ++i) {
-    const MlpTile t = mlp_decode(p, i);
+  const int total = p.n1_tiles + p.n2_tiles;
+  if (num_tiles) *num_tiles = total;
+  if (delay) *delay = p.lag_hi;
+  for (int i = 0; i < total && i < capacity; ++i) {
+    const MlpTile t = i < p.n1_tiles ? mlp_decode1(p, i) : mlp_decode2(p, i - p.n1_tiles);
     out[4 * i] = t.kind; out[4 * i + 1] = t.z; out[4 * i + 2] = t.m_blk; out[4 * i + 3] = t.n_blk;
   }
   return 0;
@@ -517,7 +610,7 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   p.b1 = b.b1; p.b2 = b.b2; p.h = b.h;
   p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
   p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
-  p.counter = sched; p.ready = sched + 1;
+  p.counter = sched; p.ready = sched + 2;
   static int hpol = -1;
   if (hpol < 0) { const char* e = getenv("GLOM_B200_MLP_HPOL"); hpol = e ? atoi(e) : 0; }      // diagnostics: 10 * store + load
   p.h_load_policy = hpol % 10; p.h_store_policy = hpol / 10;
@@ -536,7 +629,8 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
     snprintf(err, errlen, "cudaFuncSetAttribute(mlp_kernel): %s", cudaGetErrorString(e));
     return -3;
   }
-  const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
+  const int total_tiles = p.n1_tiles + p.n2_tiles;
+  const int clusters = total_tiles < max_clusters ? total_tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(MLP_THREADS);
@@ -561,17 +655,28 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
     static const char* names[16] = {"pub: wait epilogue stores", "pub: release", "tma: claim / fetch tile", "tma: dependency wait",
                                     "tma: wait smem slot", "mma: fetch tile", "mma: wait accumulator free", "mma: wait operands",
                                     "epi w0: fetch tile", "epi w0: wait accumulator", "epi w0: K1 tiles work", "epi w0: K2 tiles work",
-                                    "epi w0: publish (release)", "epi w0: kernel total", "mma: tiles", "tma: dependency waits (count)"};
+                                    "tma: K2 tiles (+ 2^32 per K1->K2 switch)", "epi w0: kernel total", "mma: tiles", "tma: dependency waits (count)"};
     std::vector<unsigned long long> h((size_t)num_sms * 16);
     if (cudaStreamSynchronize(st) == cudaSuccess &&
         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "[mlp_kernel dbg] %d tiles, delay %d row blocks, %d clusters; cycles per CTA: mean (max)\n", p.num_tiles, p.delay, clusters);
+      fprintf(stderr, "[mlp_kernel dbg] %d + %d tiles, lag thresholds %d / %d row blocks, %d clusters; cycles per CTA: mean (max)\n", p.n1_tiles, p.n2_tiles, p.lag_hi, p.lag_lo, clusters);
       for (int k = 0; k < 16; ++k) {
         double sum = 0, mx_ = 0; int cnt = 0;
         for (int c = 0; c < 2 * clusters; ++c) {
           const double v = (double)h[(size_t)c * 16 + k];
-          if (((k >= 5 && k <= 7) || k == 14) && (c & 1)) continue;     // leader-only roles
+          if (((k >= 5 && k <= 7) || k == 14 || k == 12) && (c & 1)) continue;     // leader-only roles
           sum += v; if (v > mx_) mx_ = v; ++cnt;
+        }
+        if (k == 12) {      // packed: K2 tiles in the low word, K1 -> K2 role switches in the high word
+          double k2 = 0, sw = 0, k2max = 0;
+          for (int c = 0; c < 2 * clusters; c += 2) {
+            const unsigned long long v = h[(size_t)c * 16 + k];
+            k2 += (double)(v & 0xffffffffull); sw += (double)(v >> 32);
+            if ((double)(v & 0xffffffffull) > k2max) k2max = (double)(v & 0xffffffffull);
+          }
+          fprintf(stderr, "[mlp_kernel dbg]   K2 tiles per cluster %.2f (max %.0f), K1->K2 role switches per cluster %.2f\n",
+                  k2 / clusters, k2max, sw / clusters);
+          continue;
         }
         fprintf(stderr, "[mlp_kernel dbg]   %-32s %12.0f (%12.0f)\n", names[k], cnt ? sum / cnt : 0.0, mx_);
       }

@@ -82,6 +82,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a converged warp (all 32 lanes must execute this).  Control warps run their loops warp-converged and
+// predicate the TMA / MMA instructions on the elected lane: issued from inside a divergent `if (lane == 0)` region every
+// uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR) is wrapped in an ELECT / BRA.U.ANY loop and its operands
+// are re-materialised, ~80 instructions per k-block -- measured (profiles/r2_epilogue_probe2.txt): that issue stream, not
+// the L2 feed, held the main loop at 81 % of the tensor peak; warp-converged it reaches 100 %.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (TMA/UMMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -206,6 +217,26 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m,
       "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm_sa(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(dst_smem),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_sa_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                        int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion tracking): the later TMA load of the same
+// box then hits L2 instead of waiting on HBM
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
 // same with an L2 cache policy (createpolicy value), e.g. evict-first for operands that stream through once
 __device__ __forceinline__ void tma_load_2d_2sm_hint(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
                                                      int c1, uint64_t policy) {
@@ -240,6 +271,14 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
       "[%2];" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_sa(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                   int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(dst_smem),
       "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
@@ -279,6 +318,24 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+
+// ---------------------------------------------------------------- in-kernel clock sample
+// One thread of block 0 brackets the kernel's working phase with (clock64, %globaltimer) and adds the two deltas to a
+// per-kernel accumulator: cycles / ns = the SM clock the kernel actually ran at (under the power cap this differs from
+// what NVML or a probe kernel between launches reports).  Cost: four special-register reads and two atomics per launch.
+struct ClockSample { long long c0; unsigned long long t0; };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ ClockSample clock_sample_begin() {
+  ClockSample s; s.c0 = clock64(); s.t0 = globaltimer_ns(); return s;
+}
+__device__ __forceinline__ void clock_sample_end(const ClockSample& s, unsigned long long* acc /* [2]: cycles, ns */) {
+  atomicAdd(&acc[0], (unsigned long long)(clock64() - s.c0));
+  atomicAdd(&acc[1], globaltimer_ns() - s.t0);
+}
 
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -152,13 +152,16 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
   pdl_wait();
 
   if (warp == W_TMA) {
-    if (lane == 0) {
+    // warp-converged control loop: every lane polls, the elected lane issues (see elect_one in ptx.cuh)
+    const uint32_t elected = elect_one();
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         const Tile t = decode<MODE>(p, tile);
         const int l = t.g >> 1;
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elected) {
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
@@ -213,12 +216,16 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
               }
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0 && leader) {
+    if (leader) {
+      const uint32_t elected = elect_one();
+      const uint64_t kdesc0 = umma_desc_sw128(0, 16, 1024), mdesc0 = umma_desc_sw128(0, 8192, 1024);   // K- / MN-major, address 0
       const int a_mn1 = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.a_mn : 0);
       const int b_mn1 = (MODE == BW_DW) ? 1 : (MODE == BW_BATCH ? p.b_mn : 0);
       const uint32_t idesc1 = umma_idesc_bf16(256, BN, a_mn1, b_mn1);
@@ -233,22 +240,25 @@ bwd_gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // PRE: Xb        
         for (int kb = 0; kb < t.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
-          const bool seg2 = MODE == BW_BATCH && p.k_split && kb >= p.k_split;
-          const int a_mn = seg2 ? p.a_mn2 : a_mn1, b_mn = seg2 ? p.b_mn2 : b_mn1;
-          const uint32_t idesc = seg2 ? idesc2 : idesc1;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+          if (elected) {
+            const uint32_t a_lo = smem_u32(smem + (size_t)stage * STAGE_BYTES) >> 4;
+            const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+            const bool seg2 = MODE == BW_BATCH && p.k_split && kb >= p.k_split;
+            const int a_mn = seg2 ? p.a_mn2 : a_mn1, b_mn = seg2 ? p.b_mn2 : b_mn1;
+            const uint32_t idesc = seg2 ? idesc2 : idesc1;
             // MN-major: 16 k-rows = 2048 B, the two 64-column blocks are 8192 B apart; K-major: 32 B per 16 k
-            const uint64_t ad = a_mn ? umma_desc_sw128(a_addr + k * 2048, 8192, 1024) : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = b_mn ? umma_desc_sw128(b_addr + k * 2048, 8192, 1024) : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t ad = (a_mn ? mdesc0 : kdesc0) + (uint64_t)a_lo, bd = (b_mn ? mdesc0 : kdesc0) + (uint64_t)b_lo;
+            const uint64_t ak = a_mn ? (2048 >> 4) : (32 >> 4), bk = b_mn ? (2048 >> 4) : (32 >> 4);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, ad + ak * k, bd + bk * k, idesc, 1u);
+            umma_commit_2sm(&empty_bar[stage], 3);
           }
-          umma_commit_2sm(&empty_bar[stage], 3);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull_bar[as], 3);
+        if (elected) umma_commit_2sm(&tfull_bar[as], 3);
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }

@@ -29,6 +29,11 @@ namespace glom {
 // =====================================================================================
 constexpr int GEMM_CTRL_WARPS = 4;
 
+// in-kernel clock samples (see clock_sample_begin): [kind][cycles, ns], kinds = ProfKind
+// + wait-cycle counters of block 0's control / epilogue warps: [2] MMA lane waiting for operands, [3] for a free accumulator
+// stage, [4] TMA lane waiting for a free ring slot, [5] epilogue warp 0 waiting for an accumulator, [6] its busy cycles
+__device__ unsigned long long g_kernel_clk[PROF_KINDS][8];
+
 
 struct GemmParams {
   int rows, d, L, n, G;
@@ -51,6 +56,7 @@ struct GemmParams {
   // tokeniser (MODE 2)
   float* tok_out;
   int tok_kb;      // K blocks of 64 of the zero-padded patch dimension
+  int h_prefetch;  // K2: k-blocks of H prefetched into L2 ahead of the TMA loads (0 = off)
 };
 
 template <int MODE, int BN>
@@ -187,78 +193,126 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();     // the next kernel may start its own set-up on SMs we vacate
   pdl_wait();                  // ... and we touch global memory only after the previous kernel has finished
+  const bool clk_thread = blockIdx.x == 0 && warp == W_ALLOC && lane == 0;
+  ClockSample clk_s{};
+  if (clk_thread) clk_s = clock_sample_begin();
+  const bool cnt_cta = blockIdx.x == 0;                 // wait-cycle counters: block 0 only (warp-uniform branches)
+  unsigned long long* const cnt = g_kernel_clk[MODE == 0 ? PROF_GEMM1 : MODE == 1 ? PROF_GEMM2 : PROF_TOKENIZE];
+  unsigned long long w0 = 0, w1 = 0;
+#define GLOM_CNT_WAIT(acc, stmt) do { if (cnt_cta) { const long long t_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t_); } else { stmt; } } while (0)
 
   if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
-        const TileInfo t = decode_tile<MODE>(p, tile);
-        const CUtensorMap* amap;
-        int a_col, b_row;
-        if (MODE == 0) {
-          const int l = t.z >> 1;
-          if (t.z == 0) { amap = &map_a0; a_col = 0; }                        // bottom-up level 0 reads the tokens (:132)
-          else if (t.z & 1) { amap = &map_a2; a_col = l * p.d; }              // top-down l reads S[l+1]+pos (:136)
-          else { amap = &map_a1; a_col = (l - 1) * p.d; }                     // bottom-up l reads S[l-1]   (:134)
-          b_row = t.z * 4 * p.d + t.n_blk * BN;
-        } else if (MODE == 1) {
-          amap = &map_a0; a_col = 0;             // H is stored as contiguous 16 KB (128 x 64) blocks, see below
-          b_row = t.z * p.d + t.n_blk * BN;
-        } else {
-          amap = &map_a0; a_col = 0;               // patches (rows, Kp) x Wtok (d, Kp)
-          b_row = t.n_blk * BN;
-        }
-        const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
-        b_row += (int)cta_rank * (BN / 2);
-        for (int kb = 0; kb < t.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+    // warp-converged: all lanes walk the schedule and poll the barriers, the elected lane issues (see elect_one)
+    const uint32_t elected = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t bar0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    const uint64_t pol_first = l2_policy_evict_first();
+    const int kbg_n = 4 * p.d / BK;
+    const int blk_skip = (p.m128 - 1) * kbg_n;
+    // K2: H comes from HBM (369 MB per step, written by the previous launch); the 5-slot ring covers ~2.5k clk, less
+    // than the loaded HBM latency tail, and the ring is consumed in order.  A cursor running h_prefetch k-blocks ahead
+    // of the loads (across tile boundaries) pulls the 16 KB blocks into L2 first.
+    int pf_it = 0, pf_kb = 0, pf_nkb = 0, pf_blk0 = 0;
+    bool pf_valid = false;
+    auto pf_tile = [&](int it_) {
+      pf_it = it_; pf_kb = 0;
+      const int tl = sched_tile<MODE>(p, cluster_id, num_clusters, it_);
+      pf_valid = tl >= 0;
+      if (pf_valid) {
+        const TileInfo tt = decode_tile<MODE>(p, tl);
+        pf_nkb = tt.num_kb;
+        pf_blk0 = (2 * tt.z * p.m128 + ((tt.m_blk * 256 + (int)cta_rank * BM) >> 7)) * kbg_n;
+      }
+    };
+    auto pf_step = [&]() {
+      if (!pf_valid) return;
+      const int blk = pf_blk0 + pf_kb + (pf_kb >= kbg_n ? blk_skip : 0);
+      if (elected) tma_prefetch_2d(&map_a0, 0, blk * BM);
+      if (++pf_kb == pf_nkb) pf_tile(pf_it + 1);
+    };
+    for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
+      const TileInfo t = decode_tile<MODE>(p, tile);
+      const CUtensorMap* amap;
+      int a_col, b_row;
+      if (MODE == 0) {
+        const int l = t.z >> 1;
+        if (t.z == 0) { amap = &map_a0; a_col = 0; }                        // bottom-up level 0 reads the tokens (:132)
+        else if (t.z & 1) { amap = &map_a2; a_col = l * p.d; }              // top-down l reads S[l+1]+pos (:136)
+        else { amap = &map_a1; a_col = (l - 1) * p.d; }                     // bottom-up l reads S[l-1]   (:134)
+        b_row = t.z * 4 * p.d + t.n_blk * BN;
+      } else if (MODE == 1) {
+        amap = &map_a0; a_col = 0;             // H is stored as contiguous 16 KB (128 x 64) blocks, see below
+        b_row = t.z * p.d + t.n_blk * BN;
+      } else {
+        amap = &map_a0; a_col = 0;               // patches (rows, Kp) x Wtok (d, Kp)
+        b_row = t.n_blk * BN;
+      }
+      const int a_row = t.m_blk * 256 + (int)cta_rank * BM;
+      b_row += (int)cta_rank * (BN / 2);
+      // K2: block (group g, 128-row block, 64-wide k block); [H_bu,l | H_td,l] are groups 2l and 2l+1, so k block kb
+      // of the concatenation is block blk0 + kb of group 2l and, from kb = kbg_n on, of the group behind it
+      const int blk0 = (2 * t.z * p.m128 + (a_row >> 7)) * kbg_n;
+      if (MODE == 1 && it == 0 && p.h_prefetch > 0) {            // prime the prefetch cursor
+        pf_tile(0);
+        for (int i = 0; i < p.h_prefetch; ++i) pf_step();
+      }
+      for (int kb = 0; kb < t.num_kb; ++kb) {
+        if (MODE == 1 && p.h_prefetch > 0) pf_step();
+        GLOM_CNT_WAIT(w0, mbar_wait(&empty_bar[stage], phase ^ 1));
+        if (elected) {
+          const uint32_t sa = smem0 + (uint32_t)stage * Cfg::STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land here
-          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const uint32_t bar = bar0 + 8u * (uint32_t)stage;
           if (MODE == 1) {
-            // block (group g, 128-row block, 64-wide k block): [H_bu,l | H_td,l] are groups 2l and 2l+1
-            const int kbg_n = 4 * p.d / BK;
-            const int g = 2 * t.z + (kb >= kbg_n ? 1 : 0), kbg = kb >= kbg_n ? kb - kbg_n : kb;
-            const int blk = (g * p.m128 + (a_row >> 7)) * kbg_n + kbg;
+            const int blk = blk0 + kb + (kb >= kbg_n ? blk_skip : 0);
             // H streams through once per pair of column tiles: evict-first keeps it from displacing weights / state
-            tma_load_2d_2sm_hint(sa, amap, bar, 0, blk * BM, l2_policy_evict_first());
+            tma_load_2d_2sm_sa_hint(sa, amap, bar, 0, blk * BM, pol_first);
           } else {
-            tma_load_2d_2sm(sa, amap, bar, a_col + kb * BK, a_row);
+            tma_load_2d_2sm_sa(sa, amap, bar, a_col + kb * BK, a_row);
           }
-          tma_load_2d_2sm(sa + A_STAGE_BYTES, &map_b, bar, kb * BK, b_row);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tma_load_2d_2sm_sa(sa + A_STAGE_BYTES, &map_b, bar, kb * BK, b_row);
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (cnt_cta && elected) atomicAdd(&cnt[4], w0);
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      const uint32_t elected = elect_one();
+      // descriptors of stage 0; stage s / 16-element k step k: + s * (STAGE_BYTES >> 4) + 2 k (start address field, >> 4)
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem) + A_STAGE_BYTES, 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
         const TileInfo t = decode_tile<MODE>(p, tile);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);      // both CTAs' epilogues drained this accumulator stage
+        GLOM_CNT_WAIT(w1, mbar_wait(&tempty_bar[as], aphase ^ 1));      // both CTAs' epilogues drained this accumulator stage
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < t.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          GLOM_CNT_WAIT(w0, mbar_wait(&full_bar[stage], phase));
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          if (elected) {
+            const uint64_t ad = a_desc0 + (uint64_t)(stage * (int)(Cfg::STAGE_BYTES >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(stage * (int)(Cfg::STAGE_BYTES >> 4));
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 1; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
           }
-          umma_commit_2sm(&empty_bar[stage], 3);     // frees the slot in both CTAs
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
+        if (elected) umma_commit_2sm(&tfull_bar[as], 3);          // accumulator complete -> both epilogues
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      if (cnt_cta && elected) { atomicAdd(&cnt[2], w0); atomicAdd(&cnt[3], w1); }
     }
   } else if (warp < Cfg::EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (4 * PARTS warps)
@@ -294,8 +348,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       }
       const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
       const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
-      mbar_wait(&tfull_bar[as], aphase);
+      GLOM_CNT_WAIT(w0, mbar_wait(&tfull_bar[as], aphase));
       tc_fence_after_sync();
+      const long long busy_t0 = cnt_cta ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
       const float* bias = bias_s + part * PART_COLS;
       if (MODE == 0) {
@@ -351,6 +406,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (cnt_cta) w1 += (unsigned long long)(clock64() - busy_t0);
       if (has_next) {
         named_bar_sync(1, EPI_THREADS);     // everyone is done with this tile's bias
 #pragma unroll
@@ -359,10 +415,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         named_bar_sync(1, EPI_THREADS);     // next tile's bias visible
       }
     }
+    if (cnt_cta && warp == 0 && lane == 0) { atomicAdd(&cnt[5], w0); atomicAdd(&cnt[6], w1); }
   }
+#undef GLOM_CNT_WAIT
 
   tc_fence_before_sync();
   __syncthreads();
+  if (clk_thread) clock_sample_end(clk_s, g_kernel_clk[MODE == 0 ? PROF_GEMM1 : MODE == 1 ? PROF_GEMM2 : PROF_TOKENIZE]);
   cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
   if (warp == W_ALLOC) {
     tc_fence_after_sync();
@@ -467,53 +526,72 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
+  const bool clk_thread = blockIdx.x == 0 && warp == W_ALLOC && lane == 0;
+  ClockSample clk_s{};
+  if (clk_thread) clk_s = clock_sample_begin();
 
   if (warp == W_TMA) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = cluster_id; it < p.num_items; it += num_clusters) {
-        const int b = it / pairs_per_img, l = (it % pairs_per_img) / p.npairs;
-        const int q0 = (2 * (it % p.npairs) + (int)cta_rank) * BM;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const int w = min(256, p.n_pad16 - kb * 256);
-          const int key0 = kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
-          for (int dc = 0; dc < p.d / BK; dc += cps) {
-            const int nc = min(cps, p.d / BK - dc);
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* s = stages + (size_t)stage * ATTN_SLOT_BYTES;
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)nc * (kv_off + (uint32_t)p.khalf_rows * 128u));
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+    // ------------------------------------------------------------------ TMA producer (both CTAs), warp-converged
+    // (all lanes walk the item list and poll the ring, the elected lane issues: see elect_one)
+    const uint32_t elected = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t stages0 = smem_u32(stages);
+    const uint32_t bar0 = mapa_shared(smem_u32(&full_bar[0]), 0);
+    const uint32_t qk_tx = kv_off + (uint32_t)p.khalf_rows * 128u;
+    for (int it = cluster_id; it < p.num_items; it += num_clusters) {
+      const int b = it / pairs_per_img, l = (it % pairs_per_img) / p.npairs;
+      const int q0 = (2 * (it % p.npairs) + (int)cta_rank) * BM;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int w = min(256, p.n_pad16 - kb * 256);
+        const int key0 = kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
+        for (int dc = 0; dc < p.d / BK; dc += cps) {
+          const int nc = min(cps, p.d / BK - dc);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elected) {
+            const uint32_t s = stages0 + (uint32_t)stage * ATTN_SLOT_BYTES;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)nc * qk_tx);
+            const uint32_t bar = bar0 + 8u * (uint32_t)stage;
             for (int c = 0; c < nc; ++c) {
-              if (!p.q_in_k) tma_load_3d_2sm(s, &map_q, bar, l * p.d + (dc + c) * BK, q0, b);
-              tma_load_3d_2sm(s + kv_off + c * 16384, &map_k, bar, l * p.d + (dc + c) * BK, key0, b);
+              if (!p.q_in_k) tma_load_3d_2sm_sa(s, &map_q, bar, l * p.d + (dc + c) * BK, q0, b);
+              tma_load_3d_2sm_sa(s + kv_off + c * 16384, &map_k, bar, l * p.d + (dc + c) * BK, key0, b);
             }
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        for (int sp = 0; sp < nsub; ++sp) {
-          const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;     // slice width as issued (128 or 256)
-          const int nbox = wdp >> 7;                                   // 64-column boxes in this CTA's half
-          for (int vs = 0; vs < nvslot; ++vs) {
-            const int nkc = min(2, p.nchunk - 2 * vs);               // 64-key chunks in this slot
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* s = stages + (size_t)stage * ATTN_SLOT_BYTES;
+      }
+      for (int sp = 0; sp < nsub; ++sp) {
+        const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;     // slice width as issued (128 or 256)
+        const int nbox = wdp >> 7;                                   // 64-column boxes in this CTA's half
+        for (int vs = 0; vs < nvslot; ++vs) {
+          const int nkc = min(2, p.nchunk - 2 * vs);               // 64-key chunks in this slot
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elected) {
+            const uint32_t s = stages0 + (uint32_t)stage * ATTN_SLOT_BYTES;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(nkc * nbox) * 8192u);
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            const uint32_t bar = bar0 + 8u * (uint32_t)stage;
             for (int kc = 0; kc < nkc; ++kc)
               for (int i = 0; i < nbox; ++i) {
                 const int dcol = sp * 256 + (int)cta_rank * (wdp >> 1) + i * 64;   // this CTA's half of the slice
-                tma_load_3d_2sm(s + kc * 16384 + i * 8192, &map_v, bar, dcol < p.d ? l * p.d + dcol : p.L * p.d,
-                                (2 * vs + kc) * 64, b);                            // past d: out of bounds -> zeros
+                tma_load_3d_2sm_sa(s + kc * 16384 + i * 8192, &map_v, bar, dcol < p.d ? l * p.d + dcol : p.L * p.d,
+                                   (2 * vs + kc) * 64, b);                         // past d: out of bounds -> zeros
               }
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == W_MMA) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only), warp-converged
+    if (leader) {
+      const uint32_t elected = elect_one();
+      const uint32_t stages0 = smem_u32(stages);
+      // K-major operand descriptors (Q, K halves, P) and the MN-major one of V, all relative to shared-memory offset 0:
+      // the start-address field (>> 4) of a concrete operand is added per use
+      const uint64_t kdesc0 = umma_desc_sw128(0, 16, 1024);
+      const uint64_t vdesc0 = umma_desc_sw128(0, 8192, 1024);
+      const uint32_t p_lo = smem_u32(p_smem) >> 4;
       int stage = 0; uint32_t phase = 0;
       uint32_t job = 0, item_par = 0;
       for (int it = cluster_id; it < p.num_items; it += num_clusters, item_par ^= 1) {
@@ -529,19 +607,22 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
             const int nc = min(cps, p.d / BK - dc);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after_sync();
-            const uint32_t s_addr = smem_u32(stages + (size_t)stage * ATTN_SLOT_BYTES);
-            for (int c = 0; c < nc; ++c) {
-              const uint32_t b_addr = s_addr + kv_off + (uint32_t)c * 16384u;
-              const uint32_t a_addr = p.q_in_k ? b_addr : s_addr;
+            if (elected) {
+              const uint32_t s_lo = (stages0 + (uint32_t)stage * ATTN_SLOT_BYTES) >> 4;
+              for (int c = 0; c < nc; ++c) {
+                const uint64_t bd = kdesc0 + (uint64_t)(s_lo + ((kv_off + (uint32_t)c * 16384u) >> 4));
+                const uint64_t ad = p.q_in_k ? bd : kdesc0 + (uint64_t)s_lo;
+                umma_bf16_2sm(d_tmem, ad, bd, idesc, (dc | c) != 0 ? 1u : 0u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                              umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (dc | c | k) != 0 ? 1u : 0u);
+                for (int k = 1; k < 4; ++k) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              }
+              umma_commit_2sm(&empty_bar[stage], 3);
             }
-            umma_commit_2sm(&empty_bar[stage], 3);
+            __syncwarp();
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm(&afull_bar[buf], 3);
+          if (elected) umma_commit_2sm(&afull_bar[buf], 3);
+          __syncwarp();
         }
         // phase 2: O = P V   (A = P from smem, K-major; B = V slice, MN-major, 64 columns from each CTA)
         mbar_wait_cluster(pready_bar, item_par);
@@ -557,19 +638,22 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
             const int nkc = min(2, p.nchunk - 2 * vs);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after_sync();
-            const uint32_t s_addr = smem_u32(stages + (size_t)stage * ATTN_SLOT_BYTES);
-            for (int kc = 0; kc < nkc; ++kc) {
-              const uint32_t a_addr = smem_u32(p_smem + (size_t)(2 * vs + kc) * A_STAGE_BYTES);
-              const uint32_t b_addr = s_addr + (uint32_t)kc * 16384u;
+            if (elected) {
+              const uint32_t s_lo = (stages0 + (uint32_t)stage * ATTN_SLOT_BYTES) >> 4;
+              for (int kc = 0; kc < nkc; ++kc) {
+                const uint64_t ad = kdesc0 + (uint64_t)(p_lo + (uint32_t)(2 * vs + kc) * (A_STAGE_BYTES >> 4));
+                const uint64_t bd = vdesc0 + (uint64_t)(s_lo + (uint32_t)kc * (16384u >> 4));
+                umma_bf16_2sm(d_tmem, ad, bd, idesc, (vs | kc) != 0 ? 1u : 0u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                              umma_desc_sw128(b_addr + k * 2048, 8192, 1024), idesc, (vs | kc | k) != 0 ? 1u : 0u);
+                for (int k = 1; k < 4; ++k) umma_bf16_2sm(d_tmem, ad + 2 * k, bd + (2048 >> 4) * k, idesc, 1u);
+              }
+              umma_commit_2sm(&empty_bar[stage], 3);
             }
-            umma_commit_2sm(&empty_bar[stage], 3);
+            __syncwarp();
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm(&afull_bar[buf], 3);
+          if (elected) umma_commit_2sm(&afull_bar[buf], 3);
+          __syncwarp();
         }
       }
     }
@@ -835,11 +919,22 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
 
   tc_fence_before_sync();
   __syncthreads();
+  if (clk_thread) clock_sample_end(clk_s, g_kernel_clk[PROF_ATTN]);
   cluster_sync_all();          // no CTA exits (or frees TMEM) while its pair can still touch it
   if (warp == W_ALLOC) {
     tc_fence_after_sync();
     tmem_dealloc_2sm(tmem_base, 512);
   }
+}
+
+// cycles / ns accumulated by the kernels of this translation unit since the last call (and reset)
+cudaError_t tc_kernel_clocks(unsigned long long* out /* [PROF_KINDS][8] */, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_kernel_clk, sizeof(unsigned long long) * PROF_KINDS * 8);
+  if (e == cudaSuccess && reset) {
+    static const unsigned long long zeros[PROF_KINDS * 8] = {};
+    e = cudaMemcpyToSymbol(g_kernel_clk, zeros, sizeof(zeros));
+  }
+  return e;
 }
 
 // =====================================================================================
@@ -986,6 +1081,9 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn
     p.m128 = m128;
     p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
     p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
+    static int h_pf = -1;
+    if (h_pf < 0) { const char* ev = getenv("GLOM_B200_K2_PREFETCH"); h_pf = ev ? atoi(ev) : 0; }
+    p.h_prefetch = h_pf;
     cudaError_t e;
     ProfScope scope(prof, PROF_GEMM2, st);
     if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);

@@ -401,18 +401,19 @@ def test_packed_weight_cache_follows_the_parameters():
                                   (256, 4, 64, 4, 9, 5)],
                          ids=["d256_rows192", "config2_dims_B3", "d512_L2_rows64", "config4_dims_B1", "d256_rows2304"])
 def test_merged_mlp_kernel_is_bit_identical_to_the_three_kernel_step(spec, monkeypatch):
-    """dim % 256 == 0: the step is consensus + ONE persistent MLP kernel (mlp_kernel.cu: GEMM1+GELU and GEMM2+combine
-    tiles from a dynamically scheduled list with dependency counters).  Same tiles, same accumulation order as the
-    three-kernel step (GLOM_B200_SPLIT_MLP=1), so every time step must agree bit for bit; run twice to catch races."""
+    """GLOM_B200_MERGED_MLP=1 (dim % 256 == 0): the step is consensus + ONE persistent MLP kernel (mlp_kernel.cu: GEMM1+GELU
+    and GEMM2+combine tiles drawn from two ordered lists by an adaptive scheduler, with dependency counters).  Same tiles,
+    same accumulation order as the default three-kernel step, so every time step must agree bit for bit; run twice to
+    catch races."""
     dim, L, isz, p, B, T = spec
     torch.manual_seed(21)
     m = G.Glom(dim=dim, levels=L, image_size=isz, patch_size=p).to(DEV).eval()
     img = torch.randn(B, 3, isz, isz, generator=torch.Generator().manual_seed(22)).to(DEV)
     with torch.no_grad():
-        monkeypatch.setenv("GLOM_B200_SPLIT_MLP", "1")
+        monkeypatch.delenv("GLOM_B200_MERGED_MLP", raising=False)
         ref = m(img, iters=T, return_all=True)
         launches_split = m.last_launches
-        monkeypatch.delenv("GLOM_B200_SPLIT_MLP")
+        monkeypatch.setenv("GLOM_B200_MERGED_MLP", "1")
         for _ in range(2):
             out = m(img, iters=T, return_all=True)
             assert torch.equal(out, ref)

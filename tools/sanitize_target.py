@@ -1,5 +1,5 @@
 """Small workload for compute-sanitizer that touches every tensor-core kernel of the forward: the merged persistent
-MLP kernel (dim % 256 == 0), the three-kernel step (GLOM_B200_SPLIT_MLP=1), the consensus kernel with a radius mask,
+MLP kernel (GLOM_B200_MERGED_MLP=1, dim % 256 == 0), the default three-kernel step, the consensus kernel with a radius mask,
 the tokeniser, the island analytics and one backward."""
 import os
 import sys
@@ -14,9 +14,9 @@ m = G.Glom(dim=256, levels=3, image_size=32, patch_size=4, local_consensus_radiu
 img = torch.randn(5, 3, 32, 32, device="cuda")           # 320 rows: a partial 256-row pair tile
 with torch.no_grad():
     a = m(img, iters=3, return_all=True)
-    os.environ["GLOM_B200_SPLIT_MLP"] = "1"
+    os.environ["GLOM_B200_MERGED_MLP"] = "1"
     b = m(img, iters=3, return_all=True)
-    os.environ.pop("GLOM_B200_SPLIT_MLP")
+    os.environ.pop("GLOM_B200_MERGED_MLP")
     isl = G.islands(a, threshold=0.5)
 torch.cuda.synchronize()
 assert torch.equal(a, b), "merged MLP kernel differs from the three-kernel step"
