@@ -57,6 +57,7 @@ struct GemmParams {
   float* tok_out;
   int tok_kb;      // K blocks of 64 of the zero-padded patch dimension
   int h_prefetch;  // K2: k-blocks of H prefetched into L2 ahead of the TMA loads (0 = off)
+  int epi_prefetch; // K2: L2 prefetch of the epilogue's state / consensus lines at tile start (GLOM_B200_K2_EPI_PREFETCH, default on)
 };
 
 template <int MODE, int BN>
@@ -73,8 +74,10 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator stages
   static constexpr uint32_t PATCH_BYTES = (MODE == 0) ? 2048 : 4096; // per-warp 32x32 transpose patch (bf16 | f32)
   static_assert(MODE >= 0 && MODE <= 2, "0 = GEMM1+GELU, 1 = GEMM2+combine, 2 = tokeniser");
+  // K1: one private bias slice (PART_COLS floats) per epilogue warp; K2 / tokeniser keep their 8 bias values per lane in registers
+  static constexpr uint32_t BIAS_BYTES = (MODE == 0) ? EPI_WARPS * PART_COLS * 4 : 0;
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                                       (size_t)EPI_WARPS * PATCH_BYTES + BN * 4 /*bias*/ + 256;
+                                       (size_t)EPI_WARPS * PATCH_BYTES + BIAS_BYTES + 256;
 };
 
 struct TileInfo {
@@ -95,6 +98,23 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   else t.num_kb = p.tok_kb;
   return t;
 }
+
+// Round-robin tile walk of the uniform-cost kernels (K1, tokeniser) for the epilogue warps: the same sequence as
+// sched_tile / decode_tile, advanced by mixed-radix addition instead of two integer divisions per tile and thread.
+struct RRIter {
+  int tile, n_blk, m_blk, z, dn, dm, dz, C;
+  __device__ __forceinline__ void init(const GemmParams& p, int c, int C_) {
+    C = C_; tile = c;
+    n_blk = c % p.num_n; int r = c / p.num_n; m_blk = r % p.num_m; z = p.z0 + r / p.num_m;
+    dn = C_ % p.num_n; r = C_ / p.num_n; dm = r % p.num_m; dz = r / p.num_m;
+  }
+  __device__ __forceinline__ void next(const GemmParams& p) {
+    tile += C;
+    n_blk += dn; int carry = n_blk >= p.num_n ? 1 : 0; n_blk -= carry ? p.num_n : 0;
+    m_blk += dm + carry; carry = m_blk >= p.num_m ? 1 : 0; m_blk -= carry ? p.num_m : 0;
+    z += dz + carry;
+  }
+};
 
 // Static tile schedule of cluster `c` (of `C`): the it-th tile it processes, or -1 when done.
 //   K1 / tokeniser: uniform tiles, plain round-robin.
@@ -124,7 +144,7 @@ __device__ __forceinline__ int sched_tile(const GemmParams& p, int c, int C, int
 }
 
 // ---- tokeniser epilogue chunk (image_to_tokens Linear bias, glom_pytorch.py:96): f32 out, whole 128-byte lines.
-__device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float* bias, uint8_t* patch, float* dst,
+__device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float4 b4, uint8_t* patch, float* dst,
                                           size_t pitch, int lane, int rows_left) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -132,7 +152,6 @@ __device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float* 
         make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   __syncwarp();
   const int c = lane & 7, rsub = lane >> 3;
-  const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 4);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + rsub;
@@ -143,7 +162,7 @@ __device__ __forceinline__ void tok_chunk(const uint32_t (&v)[32], const float* 
   __syncwarp();
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool CNT>
 __global__ void __launch_bounds__(GemmCfg<MODE, BN>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows, d)        K2: H (rows, G*4d)
             const __grid_constant__ CUtensorMap map_a1,   // K1: state shadow Sb (rows, L*d)
@@ -158,8 +177,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   // visible to the compiler: LDS/STS instead of generic LD/ST for every patch / bias / P access)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patches = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(patches + (size_t)Cfg::EPI_WARPS * Cfg::PATCH_BYTES);    // [BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
+  float* bias_s = reinterpret_cast<float*>(patches + (size_t)Cfg::EPI_WARPS * Cfg::PATCH_BYTES);    // K1: [EPI_WARPS][PART_COLS]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -196,7 +215,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   const bool clk_thread = blockIdx.x == 0 && warp == W_ALLOC && lane == 0;
   ClockSample clk_s{};
   if (clk_thread) clk_s = clock_sample_begin();
-  const bool cnt_cta = blockIdx.x == 0;                 // wait-cycle counters: block 0 only (warp-uniform branches)
+  const bool cnt_cta = CNT && blockIdx.x == 0;          // wait-cycle counters (diagnostic instantiation): block 0 only
   unsigned long long* const cnt = g_kernel_clk[MODE == 0 ? PROF_GEMM1 : MODE == 1 ? PROF_GEMM2 : PROF_TOKENIZE];
   unsigned long long w0 = 0, w1 = 0;
 #define GLOM_CNT_WAIT(acc, stmt) do { if (cnt_cta) { const long long t_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t_); } else { stmt; } } while (0)
@@ -317,42 +336,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
   } else if (warp < Cfg::EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (4 * PARTS warps)
     const int ew = warp;
-    const int et = threadIdx.x;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int part = ew >> 2;                  // column part of the tile
     constexpr int PART_COLS = Cfg::PART_COLS;
     uint8_t* patch = patches + (size_t)ew * Cfg::PATCH_BYTES;
     int as = 0; uint32_t aphase = 0;
-    // the next tile's bias row is fetched into registers one tile ahead, so its (L2-latency) load overlaps this
-    // tile's epilogue instead of sitting on the critical path; it is swapped into shared memory between tiles
-    auto bias_src = [&](int tile_id) -> const float* {
-      const TileInfo tt = decode_tile<MODE>(p, tile_id);
-      return (MODE == 0) ? p.bias + (size_t)tt.z * 4 * p.d + tt.n_blk * BN : p.bias + (size_t)tt.z * p.d + tt.n_blk * BN;
-    };
-    constexpr int BIAS_PER_THREAD = (BN + EPI_THREADS - 1) / EPI_THREADS;
-    if (sched_tile<MODE>(p, cluster_id, num_clusters, 0) >= 0) {
-      const float* bsrc = bias_src(sched_tile<MODE>(p, cluster_id, num_clusters, 0));
-      for (int i = et; i < BN; i += EPI_THREADS) bias_s[i] = __ldg(bsrc + i);
+    // Bias.  K1: every warp owns a slice of PART_COLS floats in shared memory (read as broadcast LDS.128 by the GELU); the
+    // next tile's slice is fetched into registers one tile ahead (its L2 latency overlaps this tile's epilogue) and
+    // swapped in behind a warp barrier -- no CTA-wide barrier, the 16 warps are free to drift apart.  K2 / tokeniser: the
+    // 2 x 4 values a lane needs are loaded into registers before the accumulator wait.
+    float* bias_w = bias_s + ew * PART_COLS;
+    RRIter rr{};
+    if (MODE != 1) rr.init(p, cluster_id, num_clusters);
+    if (MODE == 0 && rr.tile < p.num_tiles) {
+      static_assert(MODE != 0 || PART_COLS == 64, "K1: one float2 of bias per lane");
+      *reinterpret_cast<float2*>(bias_w + 2 * lane) =
+          __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)rr.z * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
+      __syncwarp();
     }
-    named_bar_sync(1, EPI_THREADS);
-    for (int it = 0, tile; (tile = sched_tile<MODE>(p, cluster_id, num_clusters, it)) >= 0; ++it) {
-      const TileInfo t = decode_tile<MODE>(p, tile);
-      float next_bias[BIAS_PER_THREAD];
-      const int next_tile = sched_tile<MODE>(p, cluster_id, num_clusters, it + 1);
-      const bool has_next = next_tile >= 0;
-      if (has_next) {
-        const float* bsrc = bias_src(next_tile);
-#pragma unroll
-        for (int i = 0; i < BIAS_PER_THREAD; ++i)
-          next_bias[i] = (et + i * EPI_THREADS < BN) ? __ldg(bsrc + et + i * EPI_THREADS) : 0.f;
+    for (int it = 0;; ++it) {
+      TileInfo t;
+      bool has_next = false;
+      float2 next_bias = make_float2(0.f, 0.f);
+      if (MODE == 1) {
+        const int tile = sched_tile<MODE>(p, cluster_id, num_clusters, it);
+        if (tile < 0) break;
+        t = decode_tile<MODE>(p, tile);
+      } else {
+        if (rr.tile >= p.num_tiles) break;
+        t.z = rr.z; t.m_blk = rr.m_blk; t.n_blk = rr.n_blk; t.num_kb = 0;
+        rr.next(p);                                  // rr now describes the NEXT tile
+        has_next = rr.tile < p.num_tiles;
+        if (MODE == 0 && has_next)
+          next_bias = __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)rr.z * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
+      }
+      float4 b4r[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      if (MODE != 0) {
+        const float* bsrc = p.bias + (MODE == 1 ? (size_t)t.z * p.d : (size_t)0) + t.n_blk * BN + part * PART_COLS + (lane & 7) * 4;
+        b4r[0] = __ldg(reinterpret_cast<const float4*>(bsrc));
+        if (PART_COLS > 32) b4r[1] = __ldg(reinterpret_cast<const float4*>(bsrc + 32));
       }
       const int row0 = t.m_blk * 256 + (int)cta_rank * BM + quad * 32;   // first row of this warp's 32-row band
       const int rows_left = p.rows - row0;                                // >= 32: whole band valid (warp-uniform)
+      if (MODE == 1 && p.epi_prefetch && lane < rows_left) {
+        // The combine reads this warp's 32 x 64 patch of the fp32 state (streamed to HBM by the previous step) and of C:
+        // pull those lines into L2 now, a whole main loop (~25 us) before the accumulator is complete, so the epilogue's
+        // dependent global loads hit L2 instead of paying the HBM latency four times per tile
+        const size_t o = ((size_t)(row0 + lane) * p.L + t.z) * p.d + t.n_blk * BN + part * PART_COLS;
+        prefetch_l2(p.s32_in + o);
+        if (PART_COLS > 32) prefetch_l2(p.s32_in + o + 32);
+        prefetch_l2(p.c_in + o);
+      }
       GLOM_CNT_WAIT(w0, mbar_wait(&tfull_bar[as], aphase));
       tc_fence_after_sync();
       const long long busy_t0 = cnt_cta ? clock64() : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + part * PART_COLS);
-      const float* bias = bias_s + part * PART_COLS;
+      const float* bias = bias_w;
       if (MODE == 0) {
         // H block (group, 128-row block, k block = this warp's 64-column part): 16 KB contiguous, row pitch 64
         const int hblk = (t.z * p.m128 + (t.m_blk * 2 + (int)cta_rank)) * (4 * p.d / BK) + t.n_blk * (BN / BK) + part;
@@ -372,7 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
-          tok_chunk(v, bias + c0, patch, trow + c0, (size_t)p.d, lane, rows_left);
+          tok_chunk(v, c0 ? b4r[1] : b4r[0], patch, trow + c0, (size_t)p.d, lane, rows_left);
         }
       } else {
         K2Chunk kc;
@@ -388,7 +427,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
           const int col = t.n_blk * BN + part * PART_COLS + c0;
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + (lane & 7) * 4);
+          const float4 b4 = c0 ? b4r[1] : b4r[0];
           if (rows_left >= 32) k2_chunk<true>(v, b4, patch, kc, col, lane, 32, rowsq);
           else k2_chunk<false>(v, b4, patch, kc, col, lane, rows_left, rowsq);
         }
@@ -407,12 +446,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (cnt_cta) w1 += (unsigned long long)(clock64() - busy_t0);
-      if (has_next) {
-        named_bar_sync(1, EPI_THREADS);     // everyone is done with this tile's bias
-#pragma unroll
-        for (int i = 0; i < BIAS_PER_THREAD; ++i)
-          if (et + i * EPI_THREADS < BN) bias_s[et + i * EPI_THREADS] = next_bias[i];
-        named_bar_sync(1, EPI_THREADS);     // next tile's bias visible
+      if (MODE == 0 && has_next) {          // (the __syncwarp above: every lane is done with this tile's slice)
+        *reinterpret_cast<float2*>(bias_w + 2 * lane) = next_bias;
+        __syncwarp();
       }
     }
     if (cnt_cta && warp == 0 && lane == 0) { atomicAdd(&cnt[5], w0); atomicAdd(&cnt[6], w1); }
@@ -940,12 +976,26 @@ cudaError_t tc_kernel_clocks(unsigned long long* out /* [PROF_KINDS][8] */, bool
 // =====================================================================================
 // Host side: tensor maps + launches for one Jacobi step
 // =====================================================================================
+template <int MODE, int BN, bool CNT>
+static cudaError_t launch_gemm_impl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
+                                    const GemmParams& p, int num_sms, cudaStream_t st);
+
 template <int MODE, int BN>
 static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
                                const GemmParams& p, int num_sms, cudaStream_t st) {
+  // GLOM_B200_WAIT_COUNTERS=1 (diagnostics): the instantiation whose block 0 accumulates its roles' wait cycles
+  static int count_waits = -1;
+  if (count_waits < 0) { const char* ev = getenv("GLOM_B200_WAIT_COUNTERS"); count_waits = (ev && ev[0] == '1') ? 1 : 0; }
+  if (count_waits) return launch_gemm_impl<MODE, BN, true>(a0, a1, a2, bm, p, num_sms, st);
+  return launch_gemm_impl<MODE, BN, false>(a0, a1, a2, bm, p, num_sms, st);
+}
+
+template <int MODE, int BN, bool CNT>
+static cudaError_t launch_gemm_impl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& bm,
+                                    const GemmParams& p, int num_sms, cudaStream_t st) {
   using Cfg = GemmCfg<MODE, BN>;
   static SmemOptIn optin;
-  if (cudaError_t e = optin.ensure(gemm_kernel<MODE, BN>, Cfg::SMEM_BYTES)) return e;
+  if (cudaError_t e = optin.ensure(gemm_kernel<MODE, BN, CNT>, Cfg::SMEM_BYTES)) return e;
   const int max_clusters = num_sms / 2;
   const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -959,7 +1009,7 @@ static cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, BN>, a0, a1, a2, bm, p);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, BN, CNT>, a0, a1, a2, bm, p);
 }
 
 // K3: consensus attention -> C
@@ -1084,6 +1134,9 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn
     static int h_pf = -1;
     if (h_pf < 0) { const char* ev = getenv("GLOM_B200_K2_PREFETCH"); h_pf = ev ? atoi(ev) : 0; }
     p.h_prefetch = h_pf;
+    static int epi_pf = -1;
+    if (epi_pf < 0) { const char* ev = getenv("GLOM_B200_K2_EPI_PREFETCH"); epi_pf = ev ? atoi(ev) : 1; }
+    p.epi_prefetch = epi_pf;
     cudaError_t e;
     ProfScope scope(prof, PROF_GEMM2, st);
     if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
