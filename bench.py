@@ -51,9 +51,15 @@ UNIT = "column-iterations/s"
 NOMINAL_FLOP_PER_CLK = 148 * 8192.0        # dense bf16: 4096 MAC/clk/SM x 148 SMs (2.25 PFLOP/s at ~1.86 GHz)
 
 
-def flops_per_col_iter(d, L, n):
-    """Tensor FLOPs per column-iteration: 16 d^2 (2L-1)/L + 4 n d   (SURVEY 8d)."""
-    return 16.0 * d * d * (2 * L - 1) / L + 4.0 * n * d
+def flops_per_col_iter(d, L, n, iters=None):
+    """Tensor FLOPs per column-iteration: 16 d^2 (2L-1)/L + 4 n d   (SURVEY 8d).  With `iters`: the FLOPs the engine
+    EXECUTES per column-iteration of a call of that many steps -- the first GEMM of MLP group 0 (bottom-up net of level 0,
+    whose input, the tokens, does not change during a call) runs in the call's first step only: 8 d^2 / L per
+    column-iteration less in the later steps.  Rooflines use the executed figure, never the larger algorithmic one."""
+    f = 16.0 * d * d * (2 * L - 1) / L + 4.0 * n * d
+    if iters:
+        f -= 8.0 * d * d / L * (iters - 1) / iters
+    return f
 
 
 def bytes_per_iter(d, L, n, B, s_state=2, s_w=2):
@@ -595,10 +601,10 @@ def main():
             lv = model(dev_imgs[1], iters=10, levels=lv)
             return model(dev_imgs[2], iters=6, levels=lv)
         ms4 = timed(chain, max(3, args.steps // 8))
-        other["configs[4]"] = entry(ms4, B * N_PATCH * L * 28, flops_per_col_iter(d, L, N_PATCH),
+        other["configs[4]"] = entry(ms4, B * N_PATCH * L * 28, flops_per_col_iter(d, L, N_PATCH, 28.0 / 3),
                                     f"3-frame continuation iters 12->10->6, batch={B}/GPU, three forward calls incl. tokeniser")
         ms_ra = timed(lambda: model(dev_imgs[0], iters=T, return_all=True), max(3, args.steps // 8))
-        other["configs[1] return_all"] = entry(ms_ra, B * N_PATCH * L * T, flops_per_col_iter(d, L, N_PATCH),
+        other["configs[1] return_all"] = entry(ms_ra, B * N_PATCH * L * T, flops_per_col_iter(d, L, N_PATCH, T),
                                                f"configs[1] with return_all=True ({T + 1} slabs written)")
         # configs[3]: dim=1024 L=8 384/16 iters=16, 8 images per GPU
         torch.manual_seed(0)
@@ -606,7 +612,7 @@ def main():
         n3 = (CFG3["image_size"] // CFG3["patch_size"]) ** 2
         img3 = torch.randn(8, 3, CFG3["image_size"], CFG3["image_size"], generator=torch.Generator().manual_seed(5)).to(dev)
         ms3 = timed(lambda: m3(img3, iters=16), max(3, args.steps // 8))
-        other["configs[3]"] = entry(ms3, 8 * n3 * CFG3["levels"] * 16, flops_per_col_iter(CFG3["dim"], CFG3["levels"], n3),
+        other["configs[3]"] = entry(ms3, 8 * n3 * CFG3["levels"] * 16, flops_per_col_iter(CFG3["dim"], CFG3["levels"], n3, 16),
                                     "dim=1024 L=8 384/16 iters=16, batch=8/GPU (the 8-GPU config's per-GPU shard)")
         del m3, img3
         torch.cuda.empty_cache()
@@ -671,11 +677,15 @@ def main():
         rows = B * N_PATCH
         G_ = 2 * L - 1
         kern = {}
-        flops = {"gemm1_gelu": 2.0 * rows * 4 * d * d * G_,
+        # executed FLOPs per launch, averaged over the T launches of a call: MLP group 0 runs in the first step only
+        merged_env = os.environ.get("GLOM_B200_MERGED_MLP", "0") == "1"
+        reuse_g0 = os.environ.get("GLOM_B200_REUSE_BU0", "1") != "0" and not merged_env
+        g1 = (G_ - (T - 1) / T) if (reuse_g0 and T > 0) else G_
+        flops = {"gemm1_gelu": 2.0 * rows * 4 * d * d * g1,
                  "gemm2_combine": 2.0 * rows * d * (8 * d * (L - 1) + 4 * d),
                  "attention": 4.0 * N_PATCH * N_PATCH * d * B * L}
-        flops["mlp_fused"] = flops["gemm1_gelu"] + flops["gemm2_combine"]
-        algo_bytes = {"gemm1_gelu": rows * d * 2 * G_ + G_ * 4 * d * d * 2 + rows * G_ * 4 * d * 2,
+        flops["mlp_fused"] = 2.0 * rows * 4 * d * d * G_ + flops["gemm2_combine"]
+        algo_bytes = {"gemm1_gelu": rows * d * 2 * g1 + g1 * 4 * d * d * 2 + rows * g1 * 4 * d * 2,
                       "gemm2_combine": rows * G_ * 4 * d * 2 + L * d * 8 * d * 2 + rows * L * d * (4 + 2 + 4 + 2 + 2),
                       # fused MLP kernel: state shadows + tokens in, weights once, fp32 state in/out, C in, shadows out
                       "mlp_fused": rows * d * 2 * G_ + (G_ * 4 * d * d + L * d * 8 * d) * 2 + rows * L * d * (4 + 2 + 4 + 2 + 2)}
@@ -702,7 +712,7 @@ def main():
         regime = "unknown" if clk is None else ("sustained" if clk < band else "burst")
         peak = peaks["burst"] if regime == "burst" else peaks["sustained"]
         ach = kern.get(dom, {}).get("tflops")
-        whole_tf = flops_per_col_iter(d, L, N_PATCH) * col_iters_step / world / (ms_dev / args.steps * 1e-3) / 1e12
+        whole_tf = flops_per_col_iter(d, L, N_PATCH, T) * col_iters_step / world / (ms_dev / args.steps * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": names.get(dom, dom), "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None,
                 "frac_of_sustained_peak": (ach / peaks["sustained"]) if ach else None,

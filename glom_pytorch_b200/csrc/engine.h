@@ -95,7 +95,10 @@ cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* i
 // one Jacobi step on tensor cores.  sched == nullptr (or dim % 256 != 0): GEMM1+GELU -> H ; consensus -> C ;
 // GEMM2+combine -> state t+1 (three launches).  Otherwise: consensus -> C, then the merged persistent MLP kernel
 // (mlp_kernel.cu; `sched` = this step's zeroed scheduler / dependency counters, mlp_sched_ints(g) ints).
-int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn enc, int num_sms, cudaStream_t st,
+// step_index: position of the step inside the forward call.  The bottom-up net of level 0 reads the tokens, which do not
+// change during a call (glom_pytorch.py:132-134), so its hidden activations (MLP group 0 of H) are computed by step 0 only
+// and re-read by GEMM2 of the later steps (three-launch path).
+int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, int step_index, EncodeTiledFn enc, int num_sms, cudaStream_t st,
               int* launches, char* err, size_t errlen, Profiler* prof);
 bool mlp_fused_supported(const Geometry& g);
 size_t mlp_sched_ints(const Geometry& g);

@@ -260,7 +260,7 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
       b.b1 = reinterpret_cast<const float*>(pw + pl.b1_off);
       b.b2 = reinterpret_cast<const float*>(pw + pl.b2_off);
       char msg[400] = "";
-      const int r = step_bf16(g, b, sched ? sched + (size_t)t * mlp_sched_ints(g) : nullptr, g_encode, di.sms, st,
+      const int r = step_bf16(g, b, sched ? sched + (size_t)t * mlp_sched_ints(g) : nullptr, t, g_encode, di.sms, st,
                               &g_launches, msg, sizeof(msg), &g_prof);
       if (r) return fail(r == -1 ? GLOM_B200_ERR_INVALID : GLOM_B200_ERR_CUDA, "step %d: %s", t, msg);
     }

@@ -1088,7 +1088,7 @@ static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiled
   return 0;
 }
 
-int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn enc, int num_sms, cudaStream_t st,
+int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, int step_index, EncodeTiledFn enc, int num_sms, cudaStream_t st,
               int* launches, char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n, rows = g.rows;
   if (sched && mlp_fused_supported(g)) {
@@ -1112,7 +1112,12 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, EncodeTiledFn
   {
     GemmParams p{};
     p.rows = rows; p.d = d; p.L = L; p.n = n; p.G = g.G;
-    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.z0 = 0; p.num_tiles = g.G * p.num_m * p.num_n;
+    // group 0 (bottom-up net of level 0) reads the tokens, which are the same in every step of a call (:132-134): its block
+    // of H is written by the call's first step and stays valid; the later steps run the other 2L - 2 groups only
+    static int reuse_g0 = -1;
+    if (reuse_g0 < 0) { const char* ev = getenv("GLOM_B200_REUSE_BU0"); reuse_g0 = ev ? atoi(ev) : 1; }
+    p.z0 = (step_index > 0 && reuse_g0 && g.G > 1) ? 1 : 0;
+    p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = (g.G - p.z0) * p.num_m * p.num_n;
     p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
     ProfScope scope(prof, PROF_GEMM1, st);
     cudaError_t e = launch_gemm<0, 256>(mx, msb, msp, mw1, p, num_sms, st);
