@@ -57,6 +57,8 @@ struct GemmParams {
   float* tok_out;
   int tok_kb;      // K blocks of 64 of the zero-padded patch dimension
   int h_prefetch;  // K2: k-blocks of H prefetched into L2 ahead of the TMA loads (0 = off)
+  int z_rev;        // K1: groups walked from G - 1 down to z0 (see step_bf16)
+  int h_keep_z;     // K1: H blocks of groups <= h_keep_z are stored with the default L2 policy instead of streaming stores
   int epi_prefetch; // K2: L2 prefetch of the epilogue's state / consensus lines at tile start (GLOM_B200_K2_EPI_PREFETCH, default on)
 };
 
@@ -92,7 +94,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
   t.n_blk = tile % p.num_n;
   const int r = tile / p.num_n;
   t.m_blk = r % p.num_m;
-  t.z = p.z0 + r / p.num_m;
+  t.z = (MODE == 0 && p.z_rev) ? p.G - 1 - r / p.num_m : p.z0 + r / p.num_m;
   if (MODE == 0) t.num_kb = p.d / BK;
   else if (MODE == 1) t.num_kb = ((t.z == p.L - 1) ? 4 * p.d : 8 * p.d) / BK;   // top level: no top-down half (:137)
   else t.num_kb = p.tok_kb;
@@ -105,7 +107,7 @@ struct RRIter {
   int tile, n_blk, m_blk, z, dn, dm, dz, C;
   __device__ __forceinline__ void init(const GemmParams& p, int c, int C_) {
     C = C_; tile = c;
-    n_blk = c % p.num_n; int r = c / p.num_n; m_blk = r % p.num_m; z = p.z0 + r / p.num_m;
+    n_blk = c % p.num_n; int r = c / p.num_n; m_blk = r % p.num_m; z = r / p.num_m;      // z: position in the group walk
     dn = C_ % p.num_n; r = C_ / p.num_n; dm = r % p.num_m; dz = r / p.num_m;
   }
   __device__ __forceinline__ void next(const GemmParams& p) {
@@ -346,12 +348,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
     // swapped in behind a warp barrier -- no CTA-wide barrier, the 16 warps are free to drift apart.  K2 / tokeniser: the
     // 2 x 4 values a lane needs are loaded into registers before the accumulator wait.
     float* bias_w = bias_s + ew * PART_COLS;
+    const uint64_t pol_keep = l2_policy_evict_normal();
     RRIter rr{};
     if (MODE != 1) rr.init(p, cluster_id, num_clusters);
     if (MODE == 0 && rr.tile < p.num_tiles) {
       static_assert(MODE != 0 || PART_COLS == 64, "K1: one float2 of bias per lane");
       *reinterpret_cast<float2*>(bias_w + 2 * lane) =
-          __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)rr.z * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
+          __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)(p.z_rev ? p.G - 1 - rr.z : p.z0 + rr.z) * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
       __syncwarp();
     }
     for (int it = 0;; ++it) {
@@ -364,11 +367,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         t = decode_tile<MODE>(p, tile);
       } else {
         if (rr.tile >= p.num_tiles) break;
-        t.z = rr.z; t.m_blk = rr.m_blk; t.n_blk = rr.n_blk; t.num_kb = 0;
+        t.z = (MODE == 0 && p.z_rev) ? p.G - 1 - rr.z : p.z0 + rr.z; t.m_blk = rr.m_blk; t.n_blk = rr.n_blk; t.num_kb = 0;
         rr.next(p);                                  // rr now describes the NEXT tile
         has_next = rr.tile < p.num_tiles;
         if (MODE == 0 && has_next)
-          next_bias = __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)rr.z * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
+          next_bias = __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)(p.z_rev ? p.G - 1 - rr.z : p.z0 + rr.z) * 4 * p.d + rr.n_blk * BN + part * PART_COLS) + lane);
       }
       float4 b4r[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
       if (MODE != 0) {
@@ -401,7 +404,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
-          if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, 32);
+          if (t.z <= p.h_keep_z) {       // read first by the GEMM2 launch that follows: keep it in L2 if it fits
+            if (rows_left >= 32) k1_chunk<true, 1>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, 32, pol_keep);
+            else k1_chunk<false, 1>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, rows_left, pol_keep);
+          } else if (rows_left >= 32) k1_chunk<true>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, 32);
           else k1_chunk<false>(v, bias + c0, patch, hrow + c0, (size_t)BK, lane, rows_left);
         }
       } else if (MODE == 2) {
@@ -1117,6 +1123,14 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, int step_inde
     static int reuse_g0 = -1;
     if (reuse_g0 < 0) { const char* ev = getenv("GLOM_B200_REUSE_BU0"); reuse_g0 = ev ? atoi(ev) : 1; }
     p.z0 = (step_index > 0 && reuse_g0 && g.G > 1) ? 1 : 0;
+    // Group order: GEMM2 of the previous step wrote the shadows level 0 first, the top level last, and this step's GEMM2
+    // reads H level 0 first.  Walking the groups from the top down reads the most recently written shadows first (L2
+    // hits) and leaves the groups GEMM2 starts with (levels 0, 1) as the last ones written; those are stored with the
+    // default L2 policy instead of streaming stores.  (GLOM_B200_K1_ORDER: bit 0 = reverse walk, bits 1.. = keep groups)
+    static int k1_order = -1;
+    if (k1_order < 0) { const char* ev = getenv("GLOM_B200_K1_ORDER"); k1_order = ev ? atoi(ev) : 0; }
+    p.z_rev = k1_order & 1;
+    p.h_keep_z = (k1_order >> 1) - 1;
     p.num_m = (rows + 255) / 256; p.num_n = 4 * d / 256; p.num_tiles = (g.G - p.z0) * p.num_m * p.num_n;
     p.bias = b.b1; p.h_out = b.h; p.m128 = m128;
     ProfScope scope(prof, PROF_GEMM1, st);
