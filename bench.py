@@ -736,6 +736,18 @@ def main():
                        "region, same sustained state; `value` / `ms_per_step` come from the un-instrumented pass",
                 "kernels": kern}
         roof["whole_step"]["frac_hbm"] = roof["whole_step"]["hbm_gbs_algorithmic"] / peaks["hbm_gbs"]
+        if traffic and kern.get(dom):
+            # the dominant kernel's HBM side: its arithmetic intensity sits at the ridge of the measured peaks, and the
+            # in-kernel counters show it waiting for operands, so both rooflines are printed
+            gbs = traffic / (kern[dom]["avg_us"] * 1e-6) / 1e9
+            roof["hbm"] = {"achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+                           "dram_bytes_per_launch": traffic,
+                           "flop_per_dram_byte": (flops.get(dom) or 0) / traffic,
+                           "ridge_flop_per_byte": peak * 1e12 / (peaks["hbm_gbs"] * 1e9),
+                           "read_write_ceiling_gbs": 3200.0,
+                           "read_write_ceiling_source": "profiles/r2_dram_pattern_probe.txt: a kernel that only reads and "
+                                                        "writes a tensor with the GEMM2 epilogue's access pattern, one "
+                                                        "512-thread CTA per SM (copy bandwidth: MEASURED_PEAKS.json)"}
         if clocks is not None:
             # the SM clock INSIDE the tensor-core kernels of the un-instrumented timed region (rank 0): cycles and
             # %globaltimer ns bracketing each kernel's working phase, summed per kernel kind
