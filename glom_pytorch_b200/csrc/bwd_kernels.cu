@@ -1,12 +1,14 @@
-// Backward of the GLOM column update (fp32, CUDA cores) -- SURVEY 8 row f2.
+// Backward of the GLOM column update -- SURVEY 8 row f2: the reverse loop, the fp32 CUDA-core kernels, and the dispatch to
+// the tensor-core GEMMs of tc_bwd_kernels.cu for the bf16 engine.
 //
 // Differentiates glom_pytorch/glom_pytorch.py:131-145 step by step in reverse, recomputing the per-step
 // intermediates (MLP pre-activations, attention probabilities) from the saved states S_0..S_T instead of
 // storing them:
 //   S_{t+1} = (S_t + BU(S_t, X) + TD(S_t + P) + C(S_t)) / c          (:141-142)
 // All contractions go through one strided, batched fp32 GEMM (NN / NT / TN are just stride choices), the rest
-// are small element-wise / row-reduction kernels.  This is the correctness-grade training path (the fp32
-// precision of the engine); a tensor-core backward is future work.
+// are small element-wise / row-reduction kernels.  With precision fp32 (or dim % 256 != 0) this file is the whole
+// backward; with precision bf16 `backward_run` sends the MLP and consensus GEMMs to tcgen05 (`mlp_backward_tc`,
+// `attn_bwd_gemm_tc`) and keeps the softmax / normalisation / bias reductions here.
 #include "engine.h"
 #include "ptx.cuh"
 

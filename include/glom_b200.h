@@ -134,8 +134,10 @@ GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch
 
 /* Backward of the column update: gradients of glom_b200_forward's loop
  * (glom_pytorch.py:123-148) with respect to tokens, pos, the initial state (or init_levels) and the
- * eight MLP tensors, given dL/d(output).  fp32 CUDA-core path; per-step intermediates are recomputed
- * from the saved states.  All d_* buffers are ACCUMULATED into (zero them first); weights and their
+ * eight MLP tensors, given dL/d(output).  Per-step intermediates are recomputed from the saved states.  precision
+ * GLOM_B200_BF16 with dim % 256 == 0: the MLP and consensus GEMMs of the reverse pass run on tcgen05 tensor cores (bf16
+ * operands, fp32 accumulation), softmax / normalisation / bias reductions in fp32 on CUDA cores; otherwise everything
+ * is fp32 on CUDA cores.  All d_* buffers are ACCUMULATED into (zero them first); weights and their
  * gradients use the reference's state_dict layout.
  *   states    (iters+1, B, n, L, d) fp32: S_0..S_T as returned by forward(return_all=1)
  *   grad_out  (iters+1, B, n, L, d) if grad_all else (B, n, L, d)
@@ -157,7 +159,8 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
  * launch stream (no synchronisation is added to the calls).  _end waits for those events and
  * returns summed milliseconds and launch counts per kernel kind:
  *   0 consensus attention, 1 GEMM1+GELU, 2 GEMM2+combine, 3 state prologue, 4 tokeniser,
- *   5 merged persistent MLP kernel (GEMM1+GELU and GEMM2+combine tiles of one step in one launch, dim % 256 == 0).
+ *   5 merged persistent MLP kernel (GEMM1+GELU and GEMM2+combine tiles of one step in one launch; only with the
+ *     environment variable GLOM_B200_MERGED_MLP=1 and dim % 256 == 0 -- the default step is three launches).
  * `kinds` is the capacity of both arrays (>= 5; kinds beyond the capacity are dropped). */
 #define GLOM_B200_PROFILE_KINDS 6
 GLOM_B200_API int glom_b200_profile_begin(void);
@@ -177,11 +180,12 @@ GLOM_B200_API int glom_b200_islands(const float* states, int slabs, int side_h, 
                                     float* cos_right, float* cos_down, float* agreement, int32_t* labels,
                                     int32_t* num_islands, void* stream);
 
-/* Diagnostics (host only, no GPU needed): the ordered work list of the merged persistent MLP kernel (dim % 256 == 0) for
- * (cfg, batch) on a device with `num_sms` SMs, as (kind, z, m_blk, n_blk) quadruples: kind 0 = GEMM1+GELU tile of MLP
- * group z (2l = bottom-up l, 2l+1 = top-down l), kind 1 = GEMM2+combine tile of level z; m_blk = 256-row block,
- * n_blk = 256-column block.  Writes min(capacity, *num_tiles) entries; *delay = row blocks by which a row block's GEMM2
- * tiles trail its GEMM1 tiles.  Every kind-1 tile appears after all kind-0 tiles it depends on (tests check it). */
+/* Diagnostics (host only, no GPU needed): the two ordered work lists of the merged persistent MLP kernel (opt-in,
+ * dim % 256 == 0) for (cfg, batch) on a device with `num_sms` SMs, the GEMM1 list followed by the GEMM2 list, as
+ * (kind, z, m_blk, n_blk) quadruples: kind 0 = GEMM1+GELU tile of MLP group z (2l = bottom-up l, 2l+1 = top-down l),
+ * kind 1 = GEMM2+combine tile of level z; m_blk = 256-row block, n_blk = 256-column block.  Writes
+ * min(capacity, *num_tiles) entries; *delay = row blocks by which the GEMM1 list's head must lead the GEMM2 list's head
+ * before a cluster coming from a GEMM1 tile takes the GEMM2 head.  Tests check that both lists are complete. */
 GLOM_B200_API int glom_b200_mlp_schedule(const glom_b200_cfg* cfg, int batch, int num_sms, int32_t* out, int capacity,
                                          int* num_tiles, int* delay);
 
