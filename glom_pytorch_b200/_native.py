@@ -16,6 +16,7 @@ EXPORTS = (
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
     "glom_b200_backward", "glom_b200_backward_workspace_bytes",
+    "glom_b200_tokenize_backward", "glom_b200_tokenize_backward_workspace_bytes",
     "glom_b200_clock_probe", "glom_b200_mlp_schedule", "glom_b200_islands", "glom_b200_kernel_clocks",
 )
 PROFILE_KINDS = ("attention", "gemm1_gelu", "gemm2_combine", "prologue", "tokenize", "mlp_fused")
@@ -80,6 +81,10 @@ def load():
     lib.glom_b200_mlp_schedule.restype = i32
     lib.glom_b200_islands.argtypes = [vp, i32, i32, i32, i32, i32, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     lib.glom_b200_islands.restype = i32
+    lib.glom_b200_tokenize_backward_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
+    lib.glom_b200_tokenize_backward_workspace_bytes.restype = i32
+    lib.glom_b200_tokenize_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.glom_b200_tokenize_backward.restype = i32
     lib.glom_b200_clock_probe.argtypes = [vp, i32, vp]
     lib.glom_b200_clock_probe.restype = i32
     lib.glom_b200_kernel_clocks.argtypes = [vp, vp, vp, i32, i32]
@@ -177,6 +182,19 @@ def backward(cfg, weight_ptrs, tokens_ptr, pos_ptr, states_ptr, grad_out_ptr, gr
     check(load().glom_b200_backward(ctypes.byref(cfg), ctypes.byref(w), tokens_ptr, pos_ptr, states_ptr,
                                     grad_out_ptr, ctypes.byref(g), batch, iters, int(grad_all), ws_ptr, ws_bytes,
                                     stream))
+
+
+def tokenize_backward_workspace_bytes(batch, h, w, patch, need_d_img):
+    n = ctypes.c_size_t(0)
+    check(load().glom_b200_tokenize_backward_workspace_bytes(batch, h, w, patch, int(bool(need_d_img)), ctypes.byref(n)))
+    return n.value
+
+
+def tokenize_backward(img_ptr, weight_ptr, d_tokens_ptr, d_weight_ptr, d_bias_ptr, d_img_ptr, batch, h, w, patch, dim,
+                      ws_ptr, ws_bytes, stream):
+    """Tokeniser backward; d_* pointers may be None (skipped); outputs are accumulated into."""
+    check(load().glom_b200_tokenize_backward(img_ptr, weight_ptr, d_tokens_ptr, d_weight_ptr, d_bias_ptr, d_img_ptr, batch, h, w,
+                                             patch, dim, ws_ptr, ws_bytes, stream))
 
 
 def clock_probe(out_ptr, spin_us, stream):

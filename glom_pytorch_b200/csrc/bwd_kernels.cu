@@ -274,6 +274,85 @@ __global__ void init_grad_kernel(int rows, int L, int d, const float* __restrict
   atomicAdd(dinit + i, acc);
 }
 
+// =====================================================================================
+// Tokeniser backward (image_to_tokens: Rearrange + Linear, glom_pytorch.py:94-97) -- fp32 on CUDA cores
+//   d_weight (d, 3p^2) += dTok^T . patches,  d_bias (d) += column sums of dTok,
+//   d_img (B, 3, H, W)  = fold(dTok . W)     (patches do not overlap: the fold is a permutation)
+// =====================================================================================
+// 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (:95): patches[r][k] with r = (b, ph, pw), k = (p1 p + p2) 3 + c
+__global__ void patchify_f32_kernel(const float* __restrict__ img, float* __restrict__ patches, int B, int H, int W, int p) {
+  const int hp = H / p, wp = W / p, k3 = 3 * p * p;
+  const size_t total = (size_t)B * hp * wp * k3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / k3;
+    const int k = (int)(i % k3);
+    const int b = (int)(r / ((size_t)hp * wp)), pr = (int)(r % ((size_t)hp * wp)), ph = pr / wp, pw = pr % wp;
+    const int c = k % 3, p12 = k / 3, p1 = p12 / p, p2 = p12 % p;
+    patches[i] = img[(((size_t)b * 3 + c) * H + ph * p + p1) * W + pw * p + p2];
+  }
+}
+// the inverse permutation: d_img[b][c][y][x] += dpatches[r][k]
+__global__ void unpatchify_add_kernel(const float* __restrict__ dpatches, float* __restrict__ dimg, int B, int H, int W, int p) {
+  const int hp = H / p, wp = W / p, k3 = 3 * p * p;
+  const size_t total = (size_t)B * 3 * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % 3), b = (int)(i / ((size_t)3 * W * H));
+    const int ph = y / p, p1 = y % p, pw = x / p, p2 = x % p;
+    const size_t r = ((size_t)b * hp + ph) * wp + pw;
+    dimg[i] += dpatches[r * k3 + (p1 * p + p2) * 3 + c];
+  }
+}
+
+size_t tokenize_backward_workspace_bytes(int B, int H, int W, int p, int need_dimg) {
+  const size_t rk = (size_t)B * (H / p) * (W / p) * 3 * p * p * sizeof(float);
+  return align_up(rk, 1024) * (need_dimg ? 2 : 1);
+}
+
+cudaError_t tokenize_backward(const float* img, const float* weight, const float* d_tokens, float* d_weight, float* d_bias,
+                              float* d_img, int B, int H, int W, int p, int d, void* workspace, cudaStream_t st, int* launches) {
+  const int rows = B * (H / p) * (W / p), k3 = 3 * p * p;
+  float* patches = static_cast<float*>(workspace);
+  float* dpatches = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)rows * k3 * sizeof(float), 1024));
+  cudaError_t e = cudaSuccess;
+  if (d_weight) {
+    const size_t total = (size_t)rows * k3;
+    const size_t want = (total + 255) / 256;
+    patchify_f32_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(img, patches, B, H, W, p);
+    if (launches) ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // d_weight (d, k3) += dTok^T (d x rows) . patches (rows x k3)
+    GemmF32 q{};
+    q.M = d; q.N = k3; q.K = rows; q.zdiv = 1;
+    q.A = {d_tokens, 1, d, 0, 0};
+    q.B = {patches, k3, 1, 0, 0};
+    q.C = {d_weight, k3, 1, 0, 0};
+    q.alpha = 1.f; q.beta = 1.f; q.bias = nullptr;
+    if ((e = gemm_f32(q, 1, st, launches)) != cudaSuccess) return e;
+  }
+  if (d_bias) {
+    dim3 grid((d + 31) / 32, 16);
+    colsum_acc_kernel<<<grid, 256, 0, st>>>(rows, d, (long long)d, d_tokens, d_bias);
+    if (launches) ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (d_img) {
+    // dpatches (rows, k3) = dTok (rows x d) . W (d x k3)
+    GemmF32 q{};
+    q.M = rows; q.N = k3; q.K = d; q.zdiv = 1;
+    q.A = {d_tokens, d, 1, 0, 0};
+    q.B = {weight, k3, 1, 0, 0};
+    q.C = {dpatches, k3, 1, 0, 0};
+    q.alpha = 1.f; q.beta = 0.f; q.bias = nullptr;
+    if ((e = gemm_f32(q, 1, st, launches)) != cudaSuccess) return e;
+    const size_t total = (size_t)B * 3 * H * W;
+    const size_t want = (total + 255) / 256;
+    unpatchify_add_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(dpatches, d_img, B, H, W, p);
+    if (launches) ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 __global__ void cast_bf16_rows(size_t n4, const float* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];

@@ -182,6 +182,10 @@ int attn_bwd_gemm_tc(const Geometry& g, const void* a_src, int a_state, int a_mn
                      const void* b2_src = nullptr, int b2_state = 0, int b2_mn = 0);
 
 BackwardLayout backward_layout(const Geometry& g, int precision);
+// tokeniser backward (fp32, CUDA cores; bwd_kernels.cu): any of d_weight / d_bias / d_img may be NULL; all ACCUMULATED into
+size_t tokenize_backward_workspace_bytes(int B, int H, int W, int p, int need_dimg);
+cudaError_t tokenize_backward(const float* img, const float* weight, const float* d_tokens, float* d_weight, float* d_bias,
+                              float* d_img, int B, int H, int W, int p, int d, void* workspace, cudaStream_t st, int* launches);
 int backward_run(const Geometry& g, const BackwardArgs& a, int precision, int iters, int grad_all, void* workspace,
                  EncodeTiledFn enc, int num_sms, cudaStream_t st, int* launches, char* err, size_t errlen);
 

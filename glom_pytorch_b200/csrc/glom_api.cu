@@ -333,6 +333,32 @@ GLOM_B200_API int glom_b200_tokenize(const float* img, const float* weight, cons
   return 0;
 }
 
+GLOM_B200_API int glom_b200_tokenize_backward_workspace_bytes(int batch, int height, int width, int patch, int need_d_img,
+                                                              size_t* out_bytes) {
+  if (!out_bytes || batch < 1 || patch < 1 || height < patch || width < patch || height % patch || width % patch)
+    return fail(GLOM_B200_ERR_INVALID, "tokeniser backward: bad arguments");
+  *out_bytes = tokenize_backward_workspace_bytes(batch, height, width, patch, need_d_img);
+  return 0;
+}
+
+GLOM_B200_API int glom_b200_tokenize_backward(const float* img, const float* weight, const float* d_tokens, float* d_weight,
+                                              float* d_bias, float* d_img, int batch, int height, int width, int patch, int dim,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!img || !weight || !d_tokens) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
+  if (batch < 1 || patch < 1 || dim < 1 || height < patch || width < patch || height % patch || width % patch)
+    return fail(GLOM_B200_ERR_INVALID, "image %dx%d is not a positive multiple of patch %d", height, width, patch);
+  DeviceInfo di{};
+  if (int r = device_info(&di)) return r;
+  const size_t need = tokenize_backward_workspace_bytes(batch, height, width, patch, d_img != nullptr);
+  if ((d_weight || d_img) && (!workspace || workspace_bytes < need))
+    return fail(GLOM_B200_ERR_WORKSPACE, "tokeniser backward workspace: need %zu bytes, got %zu", need, workspace_bytes);
+  g_launches = 0;
+  const cudaError_t e = tokenize_backward(img, weight, d_tokens, d_weight, d_bias, d_img, batch, height, width, patch, dim,
+                                          workspace, static_cast<cudaStream_t>(stream), &g_launches);
+  if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "tokeniser backward: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 GLOM_B200_API int glom_b200_backward_workspace_bytes(const glom_b200_cfg* cfg, int batch, size_t* out_bytes) {
   if (int r = check_cfg(cfg)) return r;
   if (batch < 1 || !out_bytes) return fail(GLOM_B200_ERR_INVALID, "bad batch/out_bytes");

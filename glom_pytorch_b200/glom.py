@@ -176,6 +176,43 @@ def zeros_like32(t):
     return torch.zeros(t.shape, dtype=torch.float32, device=t.device)
 
 
+class _Tokenize(torch.autograd.Function):
+    """image_to_tokens (glom_pytorch.py:94-97, :114) as a differentiable op on the engine's own kernels: forward =
+    glom_b200_tokenize (the same arithmetic with and without autograd), backward = glom_b200_tokenize_backward (fp32
+    CUDA-core GEMMs for d_weight / d_img, a column sum for d_bias).  No torch / cuBLAS kernel runs in the training step."""
+
+    @staticmethod
+    def forward(ctx, module, img, weight, bias):
+        img = img.float().contiguous()
+        ctx.module = module
+        ctx.save_for_backward(img, weight)
+        ctx.need = (img.requires_grad, weight.requires_grad, bias.requires_grad)
+        return module.tokens(img)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_tokens):
+        module = ctx.module
+        img, weight = ctx.saved_tensors
+        need_img, need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        device = img.device
+        b, _, h, w = img.shape
+        p = module.patch_size
+        d_tokens = d_tokens.to(torch.float32).contiguous()
+        wt = weight.detach().to(torch.float32).contiguous()
+        d_w = zeros_like32(wt) if need_w else None
+        d_b = torch.zeros(module.dim, dtype=torch.float32, device=device) if need_b else None
+        d_i = zeros_like32(img) if need_img else None
+        with torch.cuda.device(device):
+            ws_bytes = _native.tokenize_backward_workspace_bytes(b, h, w, p, need_img)
+            ws = module._get_workspace(ws_bytes, device, "_tok_bwd_ws")
+            _native.tokenize_backward(img.data_ptr(), wt.data_ptr(), d_tokens.data_ptr(),
+                                      None if d_w is None else d_w.data_ptr(), None if d_b is None else d_b.data_ptr(),
+                                      None if d_i is None else d_i.data_ptr(), b, h, w, p, module.dim,
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream)
+        return None, d_i, d_w, d_b
+
+
 class Glom(nn.Module):
     def __init__(self, *, dim=512, levels=6, image_size=224, patch_size=14, consensus_self=False,
                  local_consensus_radius=0, precision="bf16"):
@@ -355,10 +392,14 @@ class Glom(nn.Module):
         if not needs_grad:
             tokens = self.tokens(img)                                        # (:114) engine tokeniser
             return self._run_engine(tokens, self.pos_emb.weight[:n], levels, self.init_levels, iters, return_all)
-        # training: tokeniser and parameter views stay in autograd (plain torch ops, once per call); the loop is the
-        # engine's differentiable op
-        self._tok_launches = 0
-        tokens = self.image_to_tokens[1](self.image_to_tokens[0](img.float()))                   # (:114)
+        # training: the tokeniser and the loop are the engine's differentiable ops (the same kernels as without autograd);
+        # only the parameter views (pos_emb slice) are plain torch ops
+        lin = self.image_to_tokens[1]
+        if self.use_native_tokenizer:
+            tokens = _Tokenize.apply(self, img, lin.weight, lin.bias)                            # (:114)
+        else:
+            self._tok_launches = 0
+            tokens = lin(self.image_to_tokens[0](img.float()))
         pos = self.pos_emb.weight[:n]                                                            # (:117)
         state0 = None if levels is None else levels.to(device=img.device, dtype=torch.float32)
         return _ColumnUpdate.apply(self, iters, return_all, tokens, pos, state0, self.init_levels, *self._mlp_params())

@@ -154,6 +154,17 @@ GLOM_B200_API int glom_b200_backward(const glom_b200_cfg* cfg, const glom_b200_w
                        const glom_b200_grads* grads, int batch, int iters, int grad_all,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of glom_b200_tokenize (image_to_tokens, glom_pytorch.py:94-97; SURVEY 8 rows f1 + f2), fp32 on CUDA cores:
+ *   d_weight (dim, 3 patch^2) += d_tokens^T . patches,   d_bias (dim) += column sums of d_tokens,
+ *   d_img (B, 3, H, W) += fold(d_tokens . weight).
+ * Any of the three outputs may be NULL (skipped); they are ACCUMULATED into.  workspace: see _workspace_bytes
+ * (need_d_img = whether d_img is requested). */
+GLOM_B200_API int glom_b200_tokenize_backward_workspace_bytes(int batch, int height, int width, int patch, int need_d_img,
+                                                              size_t* out_bytes);
+GLOM_B200_API int glom_b200_tokenize_backward(const float* img, const float* weight, const float* d_tokens, float* d_weight,
+                                              float* d_bias, float* d_img, int batch, int height, int width, int patch, int dim,
+                                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Per-kernel device timing for the roofline report (bench.py).  Between _begin and _end every
  * kernel the forward/tokenize calls of THIS thread enqueue is bracketed by CUDA events on the
  * launch stream (no synchronisation is added to the calls).  _end waits for those events and
