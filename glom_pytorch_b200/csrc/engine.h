@@ -65,6 +65,8 @@ struct WorkspaceLayout {
   size_t c_bytes;
   size_t nsq_off[2];   // squared-norm partials              (rows, L, nparts) f32
   size_t nsq_bytes;
+  size_t attn_acc_off; // bf16 engine, n > 576 columns: fp32 output / (stabiliser, row sum) carried between the consensus kernel's key passes
+  size_t attn_acc_bytes;
   size_t sched_off;    // bf16 engine, merged MLP kernel: per iteration a tile counter + ready[L * row blocks] (ints)
   size_t sched_bytes;
   size_t total;
@@ -78,6 +80,7 @@ struct Bf16Buffers {
   const __nv_bfloat16* sp_in;  __nv_bfloat16* sp_out;
   const __nv_bfloat16* xb;
   __nv_bfloat16* h;  __nv_bfloat16* c;
+  float* attn_acc;                                    // n > 576 columns only: (rows, L, d) + (rows, L, 2) fp32 carried between key passes
   const float* nsq_in;  float* nsq_out;
   const float* pos;                                   // (n, d) fp32
   const __nv_bfloat16* w1;  const __nv_bfloat16* w2;  const float* b1;  const float* b2;

@@ -58,6 +58,9 @@ WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, in
   w.h_off = off; off = align_up(off + w.h_bytes, 1024);
   w.c_off = off; off = align_up(off + w.c_bytes, 1024);
   for (int i = 0; i < 2; ++i) { w.nsq_off[i] = off; off = align_up(off + w.nsq_bytes, 1024); }
+  w.attn_acc_off = off;
+  w.attn_acc_bytes = (precision == GLOM_B200_BF16 && g.n > 576) ? (state_elems + (size_t)g.rows * g.L * 2) * 4 : 0;
+  off = align_up(off + w.attn_acc_bytes, 1024);
   w.sched_off = off;
   w.sched_bytes = (precision == GLOM_B200_BF16 && mlp_fused_supported(g)) ? (size_t)iters * mlp_sched_ints(g) * sizeof(int) : 0;
   off = align_up(off + w.sched_bytes, 1024);
@@ -252,6 +255,7 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
       b.sp_in = sp[t & 1]; b.sp_out = sp[(t + 1) & 1];
       b.xb = xb;
       b.h = reinterpret_cast<__nv_bfloat16*>(ws + wl.h_off);
+      b.attn_acc = wl.attn_acc_bytes ? reinterpret_cast<float*>(ws + wl.attn_acc_off) : nullptr;
       b.c = reinterpret_cast<__nv_bfloat16*>(ws + wl.c_off);
       b.nsq_in = nsq[t & 1]; b.nsq_out = nsq[(t + 1) & 1];
       b.pos = pos;

@@ -501,6 +501,8 @@ constexpr int ATTN_MAX_KB = 4;
 constexpr uint32_t ATTN_SLOT_BYTES = 32768;       // ring slot: Q + K-half chunk(s), or 2 key chunks x 2 column boxes of V
 constexpr uint32_t ATTN_PATCH_BYTES = ATTN_SM_WARPS * 2048;
 constexpr float ATTN_BOUND_MAX = 96.f;            // log2 units
+constexpr int ATTN_SINGLE_PASS_MAX = 576;         // columns whose probabilities (128 queries x all keys) fit in shared memory
+constexpr int ATTN_PASS_KEYS = 512;               // keys per pass beyond that (two key blocks of 256)
 
 struct AttnParams {
   int n, L, d;
@@ -515,6 +517,13 @@ struct AttnParams {
   const float* nsq;                    // (rows, L, nparts) squared-norm partials of the state
   __nv_bfloat16* c_out;                // (rows, L, d)
   float scale;                         // d^-1/2 (:60)
+  // Key passes (n > 576 columns: the probabilities of a 128-query tile against ALL keys no longer fit in shared memory).
+  // One launch handles the keys [key0, key0 + nk) (the n_pad* / nkb / nchunk fields above describe THIS range); the
+  // unnormalised output and the per-row (stabiliser, row sum) are carried in fp32 scratch from pass to pass and the last
+  // pass normalises and writes C.  A single pass (key0 = 0, nk = n, first = last = 1) is the plain kernel.
+  int key0, nk, pass_first, pass_last;
+  float* o_acc;                        // (rows, L, d) fp32
+  float* ml_acc;                       // (rows, L, 2) fp32: stabiliser (log2 units), row sum
 };
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
@@ -585,7 +594,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       const int q0 = (2 * (it % p.npairs) + (int)cta_rank) * BM;
       for (int kb = 0; kb < p.nkb; ++kb) {
         const int w = min(256, p.n_pad16 - kb * 256);
-        const int key0 = kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
+        const int key0 = p.key0 + kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
         for (int dc = 0; dc < p.d / BK; dc += cps) {
           const int nc = min(cps, p.d / BK - dc);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -616,7 +625,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
               for (int i = 0; i < nbox; ++i) {
                 const int dcol = sp * 256 + (int)cta_rank * (wdp >> 1) + i * 64;   // this CTA's half of the slice
                 tma_load_3d_2sm_sa(s + kc * 16384 + i * 8192, &map_v, bar, dcol < p.d ? l * p.d + dcol : p.L * p.d,
-                                   (2 * vs + kc) * 64, b);                         // past d: out of bounds -> zeros
+                                   p.key0 + (2 * vs + kc) * 64, b);                // past d: out of bounds -> zeros
               }
           }
           __syncwarp();
@@ -722,8 +731,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       const int b_ = item / pairs_per_img, l_ = (item % pairs_per_img) / p.npairs;
       for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS) {
         float v = 0.f, bd = 0.f;
-        if (j < p.n) {
-          const float* ns = p.nsq + (((size_t)b_ * p.n + j) * p.L + l_) * p.nparts;
+        if (j < p.nk) {
+          const float* ns = p.nsq + (((size_t)b_ * p.n + p.key0 + j) * p.L + l_) * p.nparts;
           float ss = 0.f;
           if ((p.nparts & 3) == 0 && p.nparts <= 16) {      // one round trip: all partials in flight, then summed in order
             float4 q[4];
@@ -747,7 +756,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
     // key coordinates for the careful path: padding keys sit 20000 rows away, so one distance test masks them as well
     // (:67-69; without a radius every real key is at (0, 0), the query at (0, 0) and the threshold 1)
     for (int j = tid; j < p.n_pad16; j += ATTN_SM_THREADS)
-      key_hw[j] = j >= p.n ? (20000u << 16) : use_mask ? ((uint32_t)(j / p.mask_side) << 16) | (uint32_t)(j % p.mask_side) : 0u;
+      key_hw[j] = j >= p.nk ? (20000u << 16)
+                            : use_mask ? ((uint32_t)((p.key0 + j) / p.mask_side) << 16) | (uint32_t)((p.key0 + j) % p.mask_side) : 0u;
     const int d2_max = use_mask ? p.mask_d2_max : 1;
     if (part == 3) {                          // K-padding keys of the last 64-key chunk: P = 0, never written again
       for (int key = p.n_pad16; key < p.n_pad64; key += 8) {
@@ -772,7 +782,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       const int diag_blk = p.attend_self ? -1 : (q0 + quad * 32) >> 5;      // the 32 keys holding this warp's diagonals
       // logits (log2 units) of 16 keys starting at j0 (multiple of 16).  Plain blocks - no diagonal, padding or
       // radius mask, a warp-uniform property - take one multiply per key; the others a branch-free select chain.
-      auto plain = [&](int j0) -> bool { return !use_mask && j0 + 16 <= p.n && (j0 >> 5) != diag_blk; };
+      auto plain = [&](int j0) -> bool { return !use_mask && j0 + 16 <= p.nk && ((p.key0 + j0) >> 5) != diag_blk; };
       auto logits16 = [&](const uint32_t (&v)[16], int j0, float (&lg)[16]) {
         const float4* r4 = reinterpret_cast<const float4*>(rsc + j0);
         if (plain(j0)) {
@@ -792,7 +802,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
             const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int j = j0 + 4 * q + e;
+              const int j = p.key0 + j0 + 4 * q + e;                                  // global key index
               float sv = __uint_as_float(v[4 * q + e]) * rr[e];                       // (:60)
               sv = (j == diag) ? -5e-4f * LOG2E : sv;                                 // (:62-65)
               const int dh = qh - (int)(hh[e] >> 16), dw = qw - (int)(hh[e] & 0xFFFFu);
@@ -803,7 +813,26 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       };
 
       // stabiliser: the row's logit bound, or (beyond 2^BOUND_MAX, decided per warp) the exact running maximum
-      const float row_bound = qi < p.n ? bnd[item_par * p.n_pad16 + qi] : 0.f;
+      const bool multi = !(p.pass_first && p.pass_last);
+      float row_bound = 0.f;
+      if (qi < p.n) {
+        if (!multi) row_bound = bnd[item_par * p.n_pad16 + qi];
+        else {                                   // the pass's scale arrays cover its keys only: this row's norm from the partials
+          const float* ns = p.nsq + ((img_row0 + qi) * p.L + l) * p.nparts;
+          float ss = 0.f;
+          if ((p.nparts & 3) == 0 && p.nparts <= 16) {
+            float4 q4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              q4[i] = 4 * i < p.nparts ? __ldg(reinterpret_cast<const float4*>(ns) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ss = (((ss + q4[i].x) + q4[i].y) + q4[i].z) + q4[i].w;
+          } else {
+            for (int i = 0; i < p.nparts; ++i) ss += ns[i];
+          }
+          row_bound = p.scale * LOG2E * sqrtf(ss);
+        }
+      }
       const bool exact_max = __any_sync(0xffffffffu, !(row_bound <= ATTN_BOUND_MAX));
       float m_run = exact_max ? NEG_INF : row_bound, l_run = 0.f;      // l_run: this warp's column part only
       float m_used[ATTN_MAX_KB];
@@ -898,8 +927,27 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       if (lane == 0) mbar_arrive_cluster(pready_remote);
       // while P V runs: key scales of this cluster's next item (other parity; last read in the previous item)
       if (it + num_clusters < p.num_items) key_scales(it + num_clusters, item_par ^ 1);
+      // key passes: this row's carried (stabiliser, row sum), read before the barrier below (part 0 rewrites it after it)
+      const size_t acc_row = (img_row0 + (size_t)qi) * p.L + l;
+      float m_acc = NEG_INF, l_acc = 0.f;
+      if (multi && !p.pass_first && qi < p.n) {
+        const float2 ml = *reinterpret_cast<const float2*>(p.ml_acc + acc_row * 2);
+        m_acc = ml.x; l_acc = ml.y;
+      }
       named_bar_sync(2 + quad, 128);
-      const float inv_l = 1.0f / ((red[1024 + t] + red[1152 + t]) + (red[1280 + t] + red[1408 + t]));
+      const float l_pass = (red[1024 + t] + red[1152 + t]) + (red[1280 + t] + red[1408 + t]);
+      float inv_l = 1.0f / l_pass, f_old = 0.f, f_new = 1.f;
+      if (multi) {
+        // partial results of different key ranges are on different stabilisers only for rows on the exact-maximum path
+        float m_pass = exact_max ? m_run : row_bound;
+        if (l_pass == 0.f) m_pass = NEG_INF;                       // no unmasked key in this range
+        const float m_new = fmaxf(m_acc, m_pass);
+        f_old = (m_acc == NEG_INF) ? 0.f : ex2_approx(m_acc - m_new);
+        f_new = (m_pass == NEG_INF) ? 0.f : ex2_approx(m_pass - m_new);
+        const float l_new = l_acc * f_old + l_pass * f_new;
+        inv_l = p.pass_last ? 1.0f / l_new : 1.0f;
+        if (!p.pass_last && part == 0 && qi < p.n) *reinterpret_cast<float2*>(p.ml_acc + acc_row * 2) = make_float2(m_new, l_new);
+      }
 
       // output: O slice (128 x <=256) from TMEM, scaled by 1/rowsum, bf16, transposed through a 2 KB patch
       // so that stores cover 64-byte row segments
@@ -950,6 +998,21 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           tmem_ld32(t_addr + c0, cur);
           tmem_ld_wait();
+          if (multi) {
+            // this thread's row, 32 consecutive fp32 columns (128 bytes) of the carried output
+            float4* acc = reinterpret_cast<float4*>(p.o_acc + acc_row * p.d + sp * 256 + c0);
+            const bool row_ok = qi < p.n;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!p.pass_first && row_ok) o = acc[q];
+              const float4 v = make_float4(__uint_as_float(cur[4 * q]) * f_new + o.x * f_old, __uint_as_float(cur[4 * q + 1]) * f_new + o.y * f_old,
+                                           __uint_as_float(cur[4 * q + 2]) * f_new + o.z * f_old, __uint_as_float(cur[4 * q + 3]) * f_new + o.w * f_old);
+              if (!p.pass_last) { if (row_ok) acc[q] = v; }
+              else { cur[4 * q] = __float_as_uint(v.x); cur[4 * q + 1] = __float_as_uint(v.y); cur[4 * q + 2] = __float_as_uint(v.z); cur[4 * q + 3] = __float_as_uint(v.w); }
+            }
+            if (!p.pass_last) continue;
+          }
           emit32(cur, c0);
         }
         tc_fence_before_sync();
@@ -1022,75 +1085,82 @@ static cudaError_t launch_gemm_impl(const CUtensorMap& a0, const CUtensorMap& a1
 static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiledFn enc, int num_sms, cudaStream_t st,
                             int* launches, char* err, size_t errlen, Profiler* prof) {
   const int d = g.d, L = g.L, n = g.n;
-  AttnParams ap{};
-  ap.n = n; ap.L = L; ap.d = d;
-  ap.attend_self = g.attend_self; ap.mask_side = g.mask_side; ap.mask_d2_max = g.mask_d2_max;
-  ap.n_pad16 = (n + 15) / 16 * 16;
-  ap.n_pad64 = (n + 63) / 64 * 64;
-  ap.nkb = (ap.n_pad16 + 255) / 256;
-  ap.nchunk = ap.n_pad64 / 64;
-  ap.khalf_rows = (ap.n_pad16 < 256 ? ap.n_pad16 : 256) / 2;
-  ap.nparts = g.nparts;
-  ap.nsq = b.nsq_in;
-  ap.c_out = b.c;
-  ap.scale = 1.0f / sqrtf((float)d);
-  const int ntiles = (n + BM - 1) / BM;
-  ap.npairs = (ntiles + 1) / 2;
-  ap.q_in_k = ap.n_pad16 == 256;          // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
-  ap.num_items = ap.npairs * L * g.B;
-  size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
-                 ATTN_RED_FLOATS * 4 + 256;
-  const size_t max_smem = 227 * 1024;
-  int stages = 4;
-  while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
-  if (stages < 2 && ap.nkb <= ATTN_MAX_KB && fixed - ATTN_PATCH_BYTES + ATTN_SLOT_BYTES <= max_smem) {
-    // P of this many columns leaves at most one ring slot: give up the transpose patches (row-per-thread stores) so
-    // that loads and MMAs can overlap at all
-    ap.lean = 1;
-    fixed -= ATTN_PATCH_BYTES;
-    stages = 4;
-    while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
-  }
-  if (stages < 1 || ap.nkb > ATTN_MAX_KB) {
-    // more columns than the probabilities of a 128-query tile fit in shared memory (n > 576): the consensus of this
-    // step runs on CUDA cores in fp32 from the master state (correct for any n that the fp32 engine accepts, far slower)
-    ProfScope scope(prof, PROF_ATTN, st);
-    const cudaError_t e = attn_simt_bf16_out(g, b.s32_in, b.c, st, launches);
-    if (e != cudaSuccess) {
-      snprintf(err, errlen, "consensus for n = %d columns (CUDA-core path): %s", n, cudaGetErrorString(e));
-      return e == cudaErrorInvalidValue ? -1 : -3;
-    }
-    return 0;
-  }
-  ap.num_stages = stages;
-  const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
-  static SmemOptIn optin;
-  if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
-    snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+  // Up to 576 columns the probabilities of a 128-query tile against all keys fit in shared memory: one launch.  Beyond,
+  // the keys are processed in passes of ATTN_PASS_KEYS (one launch each, see AttnParams): no shape falls to CUDA cores.
+  const int npass = (n <= ATTN_SINGLE_PASS_MAX) ? 1 : (n + ATTN_PASS_KEYS - 1) / ATTN_PASS_KEYS;
+  if (npass > 1 && !b.attn_acc) {
+    snprintf(err, errlen, "consensus for n = %d columns needs the key-pass scratch buffer (workspace too old?)", n);
     return -3;
   }
   CUtensorMap mq, mk, mv;
   const uint64_t dims[3] = {(uint64_t)L * d, (uint64_t)n, (uint64_t)g.B};
   const uint64_t strides[2] = {(uint64_t)L * d * 2, (uint64_t)n * L * d * 2};
-  const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxk[3] = {(uint32_t)BK, (uint32_t)ap.khalf_rows, 1},
-                 boxv[3] = {(uint32_t)BK, 64, 1};
+  const uint32_t boxq[3] = {(uint32_t)BK, (uint32_t)BM, 1}, boxv[3] = {(uint32_t)BK, 64, 1};
   if (!encode_map(enc, &mq, b.sb_in, 3, dims, strides, boxq, err, errlen, "attn.q")) return -3;
-  if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
   if (!encode_map(enc, &mv, b.sb_in, 3, dims, strides, boxv, err, errlen, "attn.v")) return -3;
-  const int max_clusters = num_sms / 2;
-  const int clusters = ap.num_items < max_clusters ? ap.num_items : max_clusters;
-  ProfScope scope(prof, PROF_ATTN, st);
-  cudaLaunchConfig_t acfg{};
-  acfg.gridDim = dim3(2 * clusters); acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
-  cudaLaunchAttribute aattr[2];
-  aattr[0].id = cudaLaunchAttributeClusterDimension;
-  aattr[0].val.clusterDim.x = 2; aattr[0].val.clusterDim.y = 1; aattr[0].val.clusterDim.z = 1;
-  aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
-  aattr[1].val.programmaticStreamSerializationAllowed = 1;
-  acfg.attrs = aattr; acfg.numAttrs = 2;
-  const cudaError_t e = cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
-  if (launches) ++*launches;
-  if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  for (int pass = 0; pass < npass; ++pass) {
+    AttnParams ap{};
+    ap.n = n; ap.L = L; ap.d = d;
+    ap.attend_self = g.attend_self; ap.mask_side = g.mask_side; ap.mask_d2_max = g.mask_d2_max;
+    ap.key0 = npass == 1 ? 0 : pass * ATTN_PASS_KEYS;
+    ap.nk = npass == 1 ? n : (n - ap.key0 < ATTN_PASS_KEYS ? n - ap.key0 : ATTN_PASS_KEYS);
+    ap.pass_first = pass == 0; ap.pass_last = pass == npass - 1;
+    ap.o_acc = b.attn_acc;
+    ap.ml_acc = b.attn_acc ? b.attn_acc + (size_t)g.rows * L * d : nullptr;
+    ap.n_pad16 = (ap.nk + 15) / 16 * 16;
+    ap.n_pad64 = (ap.nk + 63) / 64 * 64;
+    ap.nkb = (ap.n_pad16 + 255) / 256;
+    ap.nchunk = ap.n_pad64 / 64;
+    ap.khalf_rows = (ap.n_pad16 < 256 ? ap.n_pad16 : 256) / 2;
+    ap.nparts = g.nparts;
+    ap.nsq = b.nsq_in;
+    ap.c_out = b.c;
+    ap.scale = 1.0f / sqrtf((float)d);
+    const int ntiles = (n + BM - 1) / BM;
+    ap.npairs = (ntiles + 1) / 2;
+    ap.q_in_k = npass == 1 && ap.n_pad16 == 256;    // one key block of 256: CTA r's queries are keys [128 r, 128 r + 128)
+    ap.num_items = ap.npairs * L * g.B;
+    size_t fixed = 1024 + (size_t)ap.nchunk * A_STAGE_BYTES + ATTN_PATCH_BYTES + (size_t)ap.n_pad16 * 20 +
+                   ATTN_RED_FLOATS * 4 + 256;
+    const size_t max_smem = 227 * 1024;
+    int stages = 4;
+    while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
+    if (stages < 2 && fixed - ATTN_PATCH_BYTES + ATTN_SLOT_BYTES <= max_smem) {
+      // P of this many columns leaves at most one ring slot: give up the transpose patches (row-per-thread stores) so
+      // that loads and MMAs can overlap at all
+      ap.lean = 1;
+      fixed -= ATTN_PATCH_BYTES;
+      stages = 4;
+      while (stages > 0 && fixed + (size_t)stages * ATTN_SLOT_BYTES > max_smem) --stages;
+    }
+    if (stages < 1 || ap.nkb > ATTN_MAX_KB) {
+      snprintf(err, errlen, "consensus pass of %d keys does not fit shared memory", ap.nk);
+      return -3;
+    }
+    ap.num_stages = stages;
+    const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+      return -3;
+    }
+    const uint32_t boxk[3] = {(uint32_t)BK, (uint32_t)ap.khalf_rows, 1};
+    if (!encode_map(enc, &mk, b.sb_in, 3, dims, strides, boxk, err, errlen, "attn.k")) return -3;
+    const int max_clusters = num_sms / 2;
+    const int clusters = ap.num_items < max_clusters ? ap.num_items : max_clusters;
+    ProfScope scope(prof, PROF_ATTN, st);
+    cudaLaunchConfig_t acfg{};
+    acfg.gridDim = dim3(2 * clusters); acfg.blockDim = dim3(ATTN_THREADS); acfg.dynamicSmemBytes = smem; acfg.stream = st;
+    cudaLaunchAttribute aattr[2];
+    aattr[0].id = cudaLaunchAttributeClusterDimension;
+    aattr[0].val.clusterDim.x = 2; aattr[0].val.clusterDim.y = 1; aattr[0].val.clusterDim.z = 1;
+    aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
+    aattr[1].val.programmaticStreamSerializationAllowed = 1;
+    acfg.attrs = aattr; acfg.numAttrs = 2;
+    const cudaError_t e = cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
+  }
   return 0;
 }
 

@@ -182,8 +182,10 @@ EDGE = [
     (128, 4, 64, 4, (64, 64), 1, 2, dict(local_consensus_radius=3)),   # radius mask on a 16 x 16 grid (n = 256)
     (64, 2, 8, 4, (8, 8), 1, 3, dict(consensus_self=True)),    # n = 4: a single 16-key block mostly padding
     (128, 2, 96, 4, (96, 96), 2, 1, dict(local_consensus_radius=2.5, consensus_self=True)),   # n = 576, mask + self, 5 query tiles (odd)
-    (64, 2, 64, 2, (64, 64), 1, 2, {}),                        # n = 1024 > 576: consensus on CUDA cores inside the bf16 engine
-    (128, 2, 64, 2, (40, 64), 2, 1, dict(local_consensus_radius=0)),   # n = 640 of 1024, same path, two images
+    (64, 2, 64, 2, (64, 64), 1, 2, {}),                        # n = 1024 > 576: tensor-core consensus in two key passes of 512
+    (128, 2, 64, 2, (40, 64), 2, 1, dict(local_consensus_radius=0)),   # n = 640 of 1024: passes of 512 + 128 keys, two images
+    (320, 2, 56, 2, (56, 56), 1, 2, dict(local_consensus_radius=6.5, consensus_self=True)),   # n = 784: passes 512 + 272, mask + self, d slices 256 + 64
+    (64, 2, 80, 2, (80, 80), 1, 1, {}),                        # n = 1600: four key passes (512 x 3 + 64), 13 query tiles
 ]
 
 
@@ -209,6 +211,26 @@ def test_shape_edge_cases_against_oracle(spec, precision):
         assert np.abs(out - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
     else:
         check_bf16(out, ref, spec)
+
+
+def test_key_passes_combine_exact_maximum_rows():
+    """n = 784 > 576 columns with levels of rms ~300: the consensus runs in two key passes AND every row is on the
+    exact-maximum path, so the passes' partial outputs sit on different stabilisers and are rescaled when combined
+    (consensus_self: the diagonal dominates, the result is well conditioned -> standard bf16 tolerance)."""
+    dim, L, isz, p = 128, 2, 56, 2                       # n = 784 columns
+    params = O.synth_params(dim, L, isz, p, seed=13)
+    rng = np.random.default_rng(14)
+    img = rng.standard_normal((1, 3, isz, isz)).astype(np.float32)
+    lv = (rng.standard_normal((1, 784, L, dim)) * 300).astype(np.float32)
+    ref = O.glom_forward(params, img, patch_size=p, iters=2, levels=lv, return_all=True, image_size=isz,
+                         dtype=np.float64, consensus_self=True)
+    m = G.Glom(dim=dim, levels=L, image_size=isz, patch_size=p, consensus_self=True)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m(torch.from_numpy(img).to(DEV), iters=2, levels=torch.from_numpy(lv).to(DEV), return_all=True).cpu().numpy()
+    assert np.isfinite(out).all()
+    check_bf16(out, ref, "key passes, exact-maximum rows")
 
 
 @pytest.mark.parametrize("consensus_self", [True, False])
