@@ -10,6 +10,8 @@ Tolerances
        6.3e-3 max-abs, with 2-3x head-room as hard caps)
   bf16 engine vs bf16-emulating oracle : rel-Frobenius <= 2e-3 (same roundings, different sum order)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -442,6 +444,69 @@ def test_merged_mlp_kernel_is_bit_identical_to_the_three_kernel_step(spec, monke
         assert m.last_launches == launches_split - T          # one launch fewer per iteration
         last = m(img, iters=T)                                 # ping-pong (not return_all) addressing
         assert torch.equal(last, ref[-1])
+
+
+def test_hidden_of_mlp_group_0_is_reused_across_the_steps_of_a_call(monkeypatch):
+    """The bottom-up net of level 0 reads the tokens, which do not change during a call: by default its hidden
+    activations are computed by the call's first step and re-read by the later ones.  Must be bit-identical to
+    recomputing them in every step (GLOM_B200_REUSE_BU0=0 is read when the library first decides, so the comparison
+    runs in a child process), also across two calls with different images on the same module."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, torch
+        sys.path.insert(0, %r)
+        import glom_pytorch_b200 as G
+        torch.manual_seed(31)
+        m = G.Glom(dim=256, levels=3, image_size=32, patch_size=4).cuda().eval()
+        a = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(32)).cuda()
+        b = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(33)).cuda()
+        with torch.no_grad():
+            out = torch.cat([m(a, iters=4, return_all=True), m(b, iters=3, return_all=True)])
+        torch.save(out.cpu(), sys.argv[1])
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    import tempfile
+    for flag in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, GLOM_B200_REUSE_BU0=flag)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_in_kernel_clock_samples():
+    """Every tensor-core kernel samples (clock64, %globaltimer) around its working phase: after a forward the API
+    reports a plausible SM clock and a positive in-kernel time for the three kernels of the step."""
+    torch.manual_seed(3)
+    m = G.Glom(dim=256, levels=3, image_size=32, patch_size=4).to(DEV).eval()
+    img = torch.randn(2, 3, 32, 32, device=DEV)
+    _native.kernel_clocks(reset=True)
+    with torch.no_grad():
+        m(img, iters=3)
+    clk = _native.kernel_clocks(reset=True)
+    for kind in ("attention", "gemm1_gelu", "gemm2_combine"):
+        assert kind in clk, clk
+        mhz, ms, _ = clk[kind]
+        assert 300.0 < mhz < 3000.0 and ms > 0.0, (kind, mhz, ms)
+    assert not _native.kernel_clocks(reset=False)          # reset: no samples left
+
+
+def test_tokenizer_backward_matches_torch_autograd():
+    """glom_b200_tokenize_backward (fp32 CUDA-core GEMMs + fold) against torch's autograd through Rearrange + Linear."""
+    torch.manual_seed(5)
+    for precision, tol in (("fp32", 2e-4), ("bf16", 2e-2)):
+        m = G.Glom(dim=128, levels=2, image_size=32, patch_size=4, precision=precision).to(DEV).train()
+        img = torch.randn(3, 3, 32, 32, device=DEV, requires_grad=True)
+        lin = m.image_to_tokens[1]
+        from glom_pytorch_b200.glom import _Tokenize
+        tok = _Tokenize.apply(m, img, lin.weight, lin.bias)
+        g = torch.randn_like(tok)
+        gi, gw, gb = torch.autograd.grad(tok, (img, lin.weight, lin.bias), g)
+        ref = lin(m.image_to_tokens[0](img))
+        ri, rw, rb = torch.autograd.grad(ref, (img, lin.weight, lin.bias), g)
+        assert (tok - ref).abs().max() <= tol * ref.abs().max()
+        for a, b in ((gi, ri), (gw, rw), (gb, rb)):
+            assert (a - b).abs().max() <= 2e-4 * b.abs().max().clamp_min(1.0), precision
 
 
 def test_clock_probe_reports_a_plausible_sm_clock():
