@@ -596,9 +596,13 @@ def main():
             return {"workload": what, "ms_per_step": ms, "value": col_iters * world / (ms * 1e-3), "unit": UNIT,
                     "tflops_per_gpu": tf, "frac_sustained": tf / peaks["sustained"], "frac_burst": tf / peaks["burst"]}
         # configs[4]: 3-frame continuation 12 -> 10 -> 6 with the state carried (README.md:105-111), incl. tokeniser
+        # (the carried tensor is the one the previous call returned, so the engine resumes from the shadows it still
+        # holds -- glom_b200_forward_resume -- and each next frame is tokenised on a side stream while the current one runs)
         def chain():
             lv = model(dev_imgs[0], iters=12)
+            model.stage_tokens(dev_imgs[1])
             lv = model(dev_imgs[1], iters=10, levels=lv)
+            model.stage_tokens(dev_imgs[2])
             return model(dev_imgs[2], iters=6, levels=lv)
         ms4 = timed(chain, max(3, args.steps // 8))
         other["configs[4]"] = entry(ms4, B * N_PATCH * L * 28, flops_per_col_iter(d, L, N_PATCH, 28.0 / 3),

@@ -12,7 +12,7 @@ PRECISION = {"fp32": 0, "bf16": 1}
 
 EXPORTS = (
     "glom_b200_abi_version", "glom_b200_last_error", "glom_b200_packed_weight_bytes",
-    "glom_b200_pack_weights", "glom_b200_workspace_bytes", "glom_b200_forward",
+    "glom_b200_pack_weights", "glom_b200_workspace_bytes", "glom_b200_forward", "glom_b200_forward_resume",
     "glom_b200_tokenize", "glom_b200_tokenize_workspace_bytes", "glom_b200_last_launch_count", "glom_b200_workspace_offset",
     "glom_b200_profile_begin", "glom_b200_profile_end",
     "glom_b200_backward", "glom_b200_backward_workspace_bytes",
@@ -85,6 +85,9 @@ def load():
     lib.glom_b200_tokenize_backward_workspace_bytes.restype = i32
     lib.glom_b200_tokenize_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.glom_b200_tokenize_backward.restype = i32
+    lib.glom_b200_forward_resume.argtypes = [ctypes.POINTER(Cfg), vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp, i32,
+                                             ctypes.POINTER(i32)]
+    lib.glom_b200_forward_resume.restype = i32
     lib.glom_b200_clock_probe.argtypes = [vp, i32, vp]
     lib.glom_b200_clock_probe.restype = i32
     lib.glom_b200_kernel_clocks.argtypes = [vp, vp, vp, i32, i32]
@@ -165,6 +168,15 @@ def profile_end():
     cnt = (ctypes.c_int * k)()
     check(load().glom_b200_profile_end(ms, cnt, k))
     return {name: (ms[i], cnt[i]) for i, name in enumerate(PROFILE_KINDS)}
+
+
+def forward_resume(cfg, packed_ptr, tokens_ptr, pos_ptr, state_in_ptr, out_ptr, batch, iters, return_all, ws_ptr, ws_bytes,
+                   stream, shadow_parity):
+    """glom_b200_forward_resume: returns the shadow buffer index holding the new final state's shadows."""
+    out_par = ctypes.c_int(0)
+    check(load().glom_b200_forward_resume(ctypes.byref(cfg), packed_ptr, tokens_ptr, pos_ptr, state_in_ptr, out_ptr, batch, iters,
+                                          int(bool(return_all)), ws_ptr, ws_bytes, stream, shadow_parity, ctypes.byref(out_par)))
+    return out_par.value
 
 
 def backward_workspace_bytes(cfg, batch):

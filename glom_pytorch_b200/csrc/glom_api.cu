@@ -195,9 +195,33 @@ GLOM_B200_API int glom_b200_workspace_offset(const glom_b200_cfg* cfg, int batch
   }
 }
 
+static int forward_impl(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens, const float* pos,
+                        const float* state_in, const float* init_levels, float* state_out, int batch, int iters,
+                        int return_all, void* workspace, size_t workspace_bytes, void* stream, int resume_parity);
+
 GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens, const float* pos,
                       const float* state_in, const float* init_levels, float* state_out, int batch, int iters,
                       int return_all, void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(cfg, packed_weights, tokens, pos, state_in, init_levels, state_out, batch, iters, return_all, workspace,
+                      workspace_bytes, stream, -1);
+}
+
+GLOM_B200_API int glom_b200_forward_resume(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens,
+                                           const float* pos, const float* state_in, float* state_out, int batch, int iters,
+                                           int return_all, void* workspace, size_t workspace_bytes, void* stream,
+                                           int shadow_parity, int* out_shadow_parity) {
+  if (!cfg || cfg->precision != GLOM_B200_BF16) return fail(GLOM_B200_ERR_INVALID, "forward_resume: bf16 engine only");
+  if (!state_in || (shadow_parity != 0 && shadow_parity != 1) || iters < 1)
+    return fail(GLOM_B200_ERR_INVALID, "forward_resume: need state_in, shadow_parity in {0, 1} and iters >= 1");
+  const int r = forward_impl(cfg, packed_weights, tokens, pos, state_in, nullptr, state_out, batch, iters, return_all, workspace,
+                             workspace_bytes, stream, shadow_parity);
+  if (r == 0 && out_shadow_parity) *out_shadow_parity = (shadow_parity + iters) & 1;
+  return r;
+}
+
+static int forward_impl(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens, const float* pos,
+                        const float* state_in, const float* init_levels, float* state_out, int batch, int iters,
+                        int return_all, void* workspace, size_t workspace_bytes, void* stream, int resume_parity) {
   if (int r = check_cfg(cfg)) return r;
   if (batch < 1 || iters < 0) return fail(GLOM_B200_ERR_INVALID, "batch must be >= 1 and iters >= 0");
   if (!packed_weights || !tokens || !pos || !state_out) return fail(GLOM_B200_ERR_INVALID, "a required pointer is NULL");
@@ -234,7 +258,20 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
     __nv_bfloat16* sp[2] = {reinterpret_cast<__nv_bfloat16*>(ws + wl.sp_off[0]), reinterpret_cast<__nv_bfloat16*>(ws + wl.sp_off[1])};
     float* nsq[2] = {reinterpret_cast<float*>(ws + wl.nsq_off[0]), reinterpret_cast<float*>(ws + wl.nsq_off[1])};
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + wl.xb_off);
-    cudaError_t e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
+    // resumed call (glom_b200_forward_resume): the shadows / norm partials of state_in are the ones the previous call left
+    // in buffer `p0`; the state prologue is skipped and step 0 reads the fp32 master straight from state_in
+    const bool resume = resume_parity >= 0;
+    const int p0 = resume ? resume_parity : 0;
+    cudaError_t e;
+    if (resume) {
+      e = launch_prep(g, nullptr, nullptr, pos, tokens, nullptr, nullptr, nullptr, xb, nullptr, st, &g_launches, &g_prof);
+      if (e == cudaSuccess && return_all) {       // slab 0 of the return_all form is S_0 (:126)
+        e = cudaMemcpyAsync(state_out, state_in, slab * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        ++g_launches;
+      }
+    } else {
+      e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
+    }
     if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "prep launch: %s", cudaGetErrorString(e));
     // The step is three launches (GEMM1+GELU, consensus, GEMM2+combine).  GLOM_B200_MERGED_MLP=1 (A/B experiment, kept
     // bit-identical and tested) replaces the two GEMM launches by the merged persistent MLP kernel (dim % 256 == 0): its
@@ -250,14 +287,14 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
     }
     for (int t = 0; t < iters; ++t) {
       Bf16Buffers b{};
-      b.s32_in = loc(t); b.s32_out = loc(t + 1);
-      b.sb_in = sb[t & 1]; b.sb_out = sb[(t + 1) & 1];
-      b.sp_in = sp[t & 1]; b.sp_out = sp[(t + 1) & 1];
+      b.s32_in = (resume && t == 0) ? state_in : loc(t); b.s32_out = loc(t + 1);
+      b.sb_in = sb[(t + p0) & 1]; b.sb_out = sb[(t + p0 + 1) & 1];
+      b.sp_in = sp[(t + p0) & 1]; b.sp_out = sp[(t + p0 + 1) & 1];
       b.xb = xb;
       b.h = reinterpret_cast<__nv_bfloat16*>(ws + wl.h_off);
       b.attn_acc = wl.attn_acc_bytes ? reinterpret_cast<float*>(ws + wl.attn_acc_off) : nullptr;
       b.c = reinterpret_cast<__nv_bfloat16*>(ws + wl.c_off);
-      b.nsq_in = nsq[t & 1]; b.nsq_out = nsq[(t + 1) & 1];
+      b.nsq_in = nsq[(t + p0) & 1]; b.nsq_out = nsq[(t + p0 + 1) & 1];
       b.pos = pos;
       b.w1 = reinterpret_cast<const __nv_bfloat16*>(pw + pl.w1_off);
       b.w2 = reinterpret_cast<const __nv_bfloat16*>(pw + pl.w2_off);

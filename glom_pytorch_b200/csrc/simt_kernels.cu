@@ -141,13 +141,16 @@ cudaError_t launch_prep(const Geometry& g, const float* state_in, const float* i
                         const float* tokens, float* s32_dst, __nv_bfloat16* sb, __nv_bfloat16* sp,
                         __nv_bfloat16* xb, float* nsq, cudaStream_t st, int* launches, Profiler* prof) {
   ProfScope scope(prof, PROF_PREP, st);
-  const int warps = g.rows * g.L;
-  const int block = 256, grid = (warps * 32 + block - 1) / block;
-  prep_state_kernel<<<grid, block, 0, st>>>(g.rows, g.n, g.L, g.d, g.nparts, g.part_w, state_in, init_levels, pos, s32_dst, sb,
-                                            sp, nsq);
-  if (launches) ++*launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (sb) {              // sb == NULL: the state's shadows and norm partials are already in place (resumed call): tokens only
+    const int warps = g.rows * g.L;
+    const int block = 256, grid = (warps * 32 + block - 1) / block;
+    prep_state_kernel<<<grid, block, 0, st>>>(g.rows, g.n, g.L, g.d, g.nparts, g.part_w, state_in, init_levels, pos, s32_dst, sb,
+                                              sp, nsq);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   const size_t n4 = (size_t)g.rows * g.d / 4;
   cast_bf16_kernel<<<(int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16), 256, 0, st>>>(n4, tokens, xb);
   if (launches) ++*launches;

@@ -30,6 +30,8 @@ forward to ~1e-5).
 """
 from math import sqrt
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -236,11 +238,13 @@ class Glom(nn.Module):
                                             local_consensus_radius=local_consensus_radius)
         self._packed = None          # (key, tensor)
         self._scratch = {}           # (slot, device index, stream) -> buffer, grown on demand, reused across calls
+        self._resume = None          # cross-call persistence: what the workspace still holds about the last returned state
+        self._staged = None          # tokens of the next frame computed ahead on a side stream (stage_tokens)
         self.use_native_tokenizer = True
         self.last_launches = 0
 
     # ------------------------------------------------------------------ cache hygiene
-    _SCRATCH_ATTRS = ("_packed", "_scratch", "_tok_launches")
+    _SCRATCH_ATTRS = ("_packed", "_scratch", "_tok_launches", "_resume", "_staged")
 
     def invalidate_packed(self):
         """Drop the cached packed copy of the MLP weights (needed after in-place ``param.data`` edits in eval mode)."""
@@ -249,6 +253,7 @@ class Glom(nn.Module):
     def _apply(self, fn, *args, **kwargs):                 # .to() / .cuda() / .float() ...: parameters are replaced
         self._packed = None
         self._scratch = {}
+        self._resume = self._staged = None
         return super()._apply(fn, *args, **kwargs)
 
     def _load_from_state_dict(self, *args, **kwargs):      # load_state_dict copies in place: versions bump, but be explicit
@@ -258,6 +263,7 @@ class Glom(nn.Module):
     def __getstate__(self):                                # torch.save(model) / pickle: no scratch buffers
         st = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)
         st["_packed"], st["_scratch"] = None, {}
+        st["_resume"] = st["_staged"] = None
         return st
 
     def __deepcopy__(self, memo):
@@ -270,6 +276,8 @@ class Glom(nn.Module):
                 new.__dict__[k] = None
             elif k == "_scratch":
                 new.__dict__[k] = {}
+            elif k in ("_resume", "_staged"):
+                new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
         return new
@@ -347,13 +355,57 @@ class Glom(nn.Module):
         self._tok_launches = _native.last_launch_count()
         return out
 
+    # ------------------------------------------------------------------ cross-call persistence
+    def stage_tokens(self, img):
+        """Video / multi-frame use (README.md:94-112): compute image_to_tokens of the NEXT frame now, on a side stream, so
+        that it overlaps the tail of the forward call already enqueued for the current frame.  The following
+        ``forward(img, ...)`` with this very tensor (unmodified) picks the tokens up instead of tokenising again.
+        No-grad inference only; returns nothing."""
+        if not img.is_cuda:
+            raise RuntimeError("stage_tokens needs a CUDA tensor")
+        device = img.device
+        with torch.cuda.device(device):
+            side = self._scratch.get(("_side_stream", device.index))
+            if side is None:
+                side = torch.cuda.Stream(device)
+                self._scratch[("_side_stream", device.index)] = side
+            cur = torch.cuda.current_stream(device)
+            side.wait_stream(cur)                       # the frame may still be on its way (H2D copy on the caller's stream)
+            with torch.cuda.stream(side), torch.no_grad():
+                tokens = self.tokens(img)
+                img.record_stream(side)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._staged = {"ref": weakref.ref(img), "version": img._version, "tokens": tokens, "event": ev,
+                        "weights": tuple((p.data_ptr(), p._version) for p in self.image_to_tokens[1].parameters())}
+
+    def _take_staged(self, img):
+        st, self._staged = self._staged, None
+        if st is None or st["ref"]() is not img or img._version != st["version"]:
+            return None
+        if st["weights"] != tuple((p.data_ptr(), p._version) for p in self.image_to_tokens[1].parameters()):
+            return None
+        cur = torch.cuda.current_stream(img.device)
+        cur.wait_event(st["event"])
+        st["tokens"].record_stream(cur)
+        return st["tokens"]
+
     # ------------------------------------------------------------------ engine call (no autograd)
-    def _run_engine(self, tokens, pos, state_in, init, iters, return_all):
-        """tokens (B,n,d), pos (n,d), state_in (B,n,L,d) or None, init (L,d): fp32 contiguous CUDA tensors."""
+    def _run_engine(self, tokens, pos, state_in, init, iters, return_all, allow_resume=False):
+        """tokens (B,n,d), pos (n,d), state_in (B,n,L,d) or None, init (L,d): fp32 contiguous CUDA tensors.
+        allow_resume (eval, no autograd): when `state_in` IS the tensor the previous call returned, unmodified, and the
+        workspace is the same, the engine still holds that state's bf16 shadows / norm partials: the state prologue is
+        skipped (glom_b200_forward_resume)."""
         device = tokens.device
         b, n = tokens.shape[0], tokens.shape[1]
+        resume, self._resume = self._resume, None
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
+            pos_key = (self.pos_emb.weight.data_ptr(), self.pos_emb.weight._version)
+            call_key = (device.index, stream, b, n, self.precision, pos_key)
+            use_resume = (allow_resume and resume is not None and state_in is not None and iters >= 1
+                          and self.precision == "bf16" and resume["ref"]() is state_in
+                          and state_in._version == resume["version"] and resume["key"] == call_key)
             tokens = tokens.detach().to(torch.float32).contiguous()
             pos = pos.detach().to(torch.float32).contiguous()
             init = init.detach().to(torch.float32).contiguous()
@@ -365,10 +417,19 @@ class Glom(nn.Module):
             out = torch.empty(((iters + 1,) + shape) if return_all else shape, dtype=torch.float32, device=device)
             ws_bytes = _native.workspace_bytes(cfg, b, iters, return_all)
             ws = self._get_workspace(ws_bytes, device)
-            _native.forward(cfg, packed.data_ptr(), tokens.data_ptr(), pos.data_ptr(),
-                            None if state_in is None else state_in.data_ptr(), init.data_ptr(),
-                            out.data_ptr(), b, iters, return_all, ws.data_ptr(), ws.numel(), stream)
+            parity = iters & 1
+            if use_resume and ws.data_ptr() == resume["ws"]:
+                parity = _native.forward_resume(cfg, packed.data_ptr(), tokens.data_ptr(), pos.data_ptr(), state_in.data_ptr(),
+                                                out.data_ptr(), b, iters, return_all, ws.data_ptr(), ws.numel(), stream,
+                                                resume["parity"])
+            else:
+                _native.forward(cfg, packed.data_ptr(), tokens.data_ptr(), pos.data_ptr(),
+                                None if state_in is None else state_in.data_ptr(), init.data_ptr(),
+                                out.data_ptr(), b, iters, return_all, ws.data_ptr(), ws.numel(), stream)
             self.last_launches = _native.last_launch_count() + getattr(self, "_tok_launches", 0)
+            if allow_resume and not return_all and iters >= 1 and self.precision == "bf16":
+                self._resume = {"ref": weakref.ref(out), "version": out._version, "key": call_key, "ws": ws.data_ptr(),
+                                "parity": parity}
         return out
 
     # ------------------------------------------------------------------ the reference's forward (:110)
@@ -390,8 +451,11 @@ class Glom(nn.Module):
         if levels is not None and tuple(levels.shape) != (b, n, self.levels, self.dim):          # (:123)
             raise RuntimeError(f"levels must have shape {(b, n, self.levels, self.dim)}, got {tuple(levels.shape)}")
         if not needs_grad:
-            tokens = self.tokens(img)                                        # (:114) engine tokeniser
-            return self._run_engine(tokens, self.pos_emb.weight[:n], levels, self.init_levels, iters, return_all)
+            tokens = self._take_staged(img)
+            if tokens is None:
+                tokens = self.tokens(img)                                    # (:114) engine tokeniser
+            return self._run_engine(tokens, self.pos_emb.weight[:n], levels, self.init_levels, iters, return_all,
+                                    allow_resume=not self.training)
         # training: the tokeniser and the loop are the engine's differentiable ops (the same kernels as without autograd);
         # only the parameter views (pos_emb slice) are plain torch ops
         lin = self.image_to_tokens[1]

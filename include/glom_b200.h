@@ -106,6 +106,19 @@ GLOM_B200_API int glom_b200_forward(const glom_b200_cfg* cfg, const void* packed
                       const float* init_levels, float* state_out, int batch, int iters,
                       int return_all, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Cross-call persistence (README.md:94-112: levels carried from frame to frame).  Same as
+ * glom_b200_forward with a carried-in state, for the case that `state_in` is bit for bit the FINAL state the previous
+ * glom_b200_forward / _forward_resume call on this workspace wrote (same cfg, batch, and `pos`): the workspace then still
+ * holds that state's bf16 shadows and norm partials in shadow buffer `shadow_parity` (0 after a plain forward with an even
+ * number of steps, 1 after an odd one; in general what the previous _resume call returned), so the state prologue is
+ * skipped and step 0 reads the fp32 master straight from `state_in`.  bf16 engine, iters >= 1.  *out_shadow_parity = the
+ * buffer holding the new final state's shadows.  Passing a state that does not match the workspace gives wrong results;
+ * the host side (glom.py) checks tensor identity and version before taking this path. */
+GLOM_B200_API int glom_b200_forward_resume(const glom_b200_cfg* cfg, const void* packed_weights, const float* tokens,
+                                           const float* pos, const float* state_in, float* state_out, int batch, int iters,
+                                           int return_all, void* workspace, size_t workspace_bytes, void* stream,
+                                           int shadow_parity, int* out_shadow_parity);
+
 /* Tokeniser, the step before the loop: replaces image_to_tokens
  * (glom_pytorch.py:94-97, call :114): patchify 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
  * fused with the Linear(3*p*p -> d).

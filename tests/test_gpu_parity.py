@@ -474,6 +474,37 @@ def test_hidden_of_mlp_group_0_is_reused_across_the_steps_of_a_call(monkeypatch)
     assert torch.equal(outs[0], outs[1])
 
 
+def test_resumed_chain_and_staged_tokens_are_bit_identical_to_the_plain_calls():
+    """SURVEY 8 row f3 (README.md:94-112, three frames, levels carried).  Passing the very tensor the previous call
+    returned lets the engine resume from the bf16 shadows / norm partials it still holds (no state prologue), and
+    `stage_tokens` computes the next frame's tokens on a side stream; both must give bit-identical states to plain calls
+    on cloned inputs (which take the ordinary prologue), for even and odd step counts, and a modified carried tensor must
+    fall back to the ordinary path."""
+    torch.manual_seed(41)
+    m = G.Glom(dim=256, levels=3, image_size=32, patch_size=4).to(DEV).eval()
+    frames = [torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(50 + i)).to(DEV) for i in range(4)]
+    with torch.no_grad():
+        ref = None                                            # ordinary path: every carried state is a fresh clone
+        refs = []
+        for f, it in zip(frames, (5, 4, 3, 2)):
+            ref = m(f.clone(), iters=it, levels=None if ref is None else ref.clone())
+            refs.append(ref)
+        launches_plain = m.last_launches
+        lv = m(frames[0], iters=5)
+        outs = [lv]
+        for k, it in ((1, 4), (2, 3), (3, 2)):
+            m.stage_tokens(frames[k])
+            lv = m(frames[k], iters=it, levels=lv)            # resumed (odd -> even -> odd shadow parity) + staged tokens
+            outs.append(lv)
+        assert m.last_launches < launches_plain               # no state prologue kernel in the resumed call
+        for a, b in zip(outs, refs):
+            assert torch.equal(a, b)
+        touched = outs[-1]
+        touched.mul_(1.0)                                     # version bump: must not resume
+        again = m(frames[0], iters=2, levels=touched)
+        assert torch.equal(again, m(frames[0].clone(), iters=2, levels=touched.clone()))
+
+
 def test_in_kernel_clock_samples():
     """Every tensor-core kernel samples (clock64, %globaltimer) around its working phase: after a forward the API
     reports a plausible SM clock and a positive in-kernel time for the three kernels of the step."""
