@@ -76,6 +76,7 @@ WorkspaceLayout workspace_layout(const Geometry& g, int precision, int iters, in
 // ---- launchers (return cudaError_t of the launch; all asynchronous on `st`) -----------------
 struct Bf16Buffers {
   const float* s32_in;  float* s32_out;              // fp32 master state of step t / t+1
+  int s32_in_bcast;                                   // 1: s32_in is init_levels (L, d) broadcast over the rows (step 0, no carried state)
   const __nv_bfloat16* sb_in;  __nv_bfloat16* sb_out;
   const __nv_bfloat16* sp_in;  __nv_bfloat16* sp_out;
   const __nv_bfloat16* xb;

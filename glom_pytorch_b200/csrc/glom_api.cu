@@ -262,6 +262,7 @@ static int forward_impl(const glom_b200_cfg* cfg, const void* packed_weights, co
     // in buffer `p0`; the state prologue is skipped and step 0 reads the fp32 master straight from state_in
     const bool resume = resume_parity >= 0;
     const int p0 = resume ? resume_parity : 0;
+    const bool s0_direct = resume || (!return_all && iters >= 1);
     cudaError_t e;
     if (resume) {
       e = launch_prep(g, nullptr, nullptr, pos, tokens, nullptr, nullptr, nullptr, xb, nullptr, st, &g_launches, &g_prof);
@@ -270,7 +271,10 @@ static int forward_impl(const glom_b200_cfg* cfg, const void* packed_weights, co
         ++g_launches;
       }
     } else {
-      e = launch_prep(g, state_in, init_levels, pos, tokens, loc(0), sb[0], sp[0], xb, nsq[0], st, &g_launches, &g_prof);
+      // S_0 as an fp32 slab is only materialised when it is part of the result (return_all slab 0, iters == 0): otherwise
+      // step 0 reads the carried state from the caller's tensor, or init_levels broadcast over the rows
+      e = launch_prep(g, state_in, init_levels, pos, tokens, s0_direct ? nullptr : loc(0), sb[0], sp[0], xb, nsq[0], st,
+                      &g_launches, &g_prof);
     }
     if (e != cudaSuccess) return fail(GLOM_B200_ERR_CUDA, "prep launch: %s", cudaGetErrorString(e));
     // The step is three launches (GEMM1+GELU, consensus, GEMM2+combine).  GLOM_B200_MERGED_MLP=1 (A/B experiment, kept
@@ -287,7 +291,8 @@ static int forward_impl(const glom_b200_cfg* cfg, const void* packed_weights, co
     }
     for (int t = 0; t < iters; ++t) {
       Bf16Buffers b{};
-      b.s32_in = (resume && t == 0) ? state_in : loc(t); b.s32_out = loc(t + 1);
+      b.s32_in = (s0_direct && t == 0) ? (state_in ? state_in : init_levels) : loc(t); b.s32_out = loc(t + 1);
+      b.s32_in_bcast = (s0_direct && t == 0 && !state_in) ? 1 : 0;
       b.sb_in = sb[(t + p0) & 1]; b.sb_out = sb[(t + p0 + 1) & 1];
       b.sp_in = sp[(t + p0) & 1]; b.sp_out = sp[(t + p0 + 1) & 1];
       b.xb = xb;

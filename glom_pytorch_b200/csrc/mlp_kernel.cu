@@ -65,7 +65,7 @@ struct MlpParams {
   const float* b1;           // (G * 4d)
   const float* b2;           // (L * d)   b2bu + b2td
   __nv_bfloat16* h;
-  const float* s32_in;  const __nv_bfloat16* c_in;  const float* pos;
+  const float* s32_in;  int s_bcast;  const __nv_bfloat16* c_in;  const float* pos;
   float* s32_out;  __nv_bfloat16* sb_out;  __nv_bfloat16* sp_out;  float* nsq_out;
   int nparts;
   int* counter;              // [2] heads of the K1 and K2 lists of this launch (zeroed by the caller)
@@ -449,8 +449,10 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         // in the list stall on the undrained accumulator stage).
         if (lane < rows_left) {
           const size_t o = ((size_t)(row0 + lane) * p.L + t.z) * p.d + t.n_blk * BN + part * PART_COLS;
-          prefetch_l2(p.s32_in + o);
-          prefetch_l2(p.s32_in + o + 32);
+          if (!p.s_bcast) {
+            prefetch_l2(p.s32_in + o);
+            prefetch_l2(p.s32_in + o + 32);
+          }
           prefetch_l2(p.c_in + o);
         }
       }
@@ -472,7 +474,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap map_x,    // tokens Xb (rows, d)
         }
       } else {
         K2Chunk kc;
-        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0; kc.prow0 = row0 % p.n;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0; kc.prow0 = row0 % p.n; kc.s_bcast = p.s_bcast;
         kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
         kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
         float rowsq[8];
@@ -608,7 +610,7 @@ int step_bf16_mlp_fused(const Geometry& g, const Bf16Buffers& b, int* sched, Enc
   mlp_list_params(g, num_sms, &p);
   const int max_clusters = num_sms / 2;
   p.b1 = b.b1; p.b2 = b.b2; p.h = b.h;
-  p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+  p.s32_in = b.s32_in; p.s_bcast = b.s32_in_bcast; p.c_in = b.c; p.pos = b.pos;
   p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
   p.counter = sched; p.ready = sched + 2;
   static int hpol = -1;

@@ -70,6 +70,7 @@ __device__ __forceinline__ void k1_chunk(const uint32_t (&v)[32], const float* b
 struct K2Chunk {
   int l, L, d, n, row0;
   int prow0;            // row0 % n: patch index of the band's first row (position table row), computed once per tile
+  int s_bcast;          // 1: s32_in is init_levels (L, d), the same for every row (first step of a call without carried state)
   const float* s32_in; const __nv_bfloat16* c_in; const float* pos;
   float* s32_out; __nv_bfloat16* sb_out; __nv_bfloat16* sp_out;
 };
@@ -96,7 +97,8 @@ __device__ __forceinline__ void k2_chunk(const uint32_t (&v)[32], const float4 b
       const int r = (h * 4 + j) * 4 + rsub;
       sv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pp[j] = sv[j]; cw[j] = make_uint2(0u, 0u);
       if (FULL || r < rows_left) {
-        sv[j] = __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
+        sv[j] = k.s_bcast ? __ldg(reinterpret_cast<const float4*>(k.s32_in + (size_t)k.l * k.d + col + c * 4))
+                          : __ldcs(reinterpret_cast<const float4*>(k.s32_in + base + (size_t)r * ld));
         cw[j] = __ldcs(reinterpret_cast<const uint2*>(k.c_in + base + (size_t)r * ld));
         if (has_td) {
           int pr = k.prow0 + r;                       // (row0 + r) % n without a division per row (r < 32)

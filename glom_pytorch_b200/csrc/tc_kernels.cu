@@ -46,6 +46,7 @@ struct GemmParams {
   __nv_bfloat16* h_out;
   // K2
   const float* s32_in;
+  int s_bcast;                       // s32_in = init_levels broadcast (see K2Chunk)
   const __nv_bfloat16* c_in;
   const float* pos;
   float* s32_out;
@@ -386,8 +387,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         // pull those lines into L2 now, a whole main loop (~25 us) before the accumulator is complete, so the epilogue's
         // dependent global loads hit L2 instead of paying the HBM latency four times per tile
         const size_t o = ((size_t)(row0 + lane) * p.L + t.z) * p.d + t.n_blk * BN + part * PART_COLS;
-        prefetch_l2(p.s32_in + o);
-        if (PART_COLS > 32) prefetch_l2(p.s32_in + o + 32);
+        if (!p.s_bcast) {
+          prefetch_l2(p.s32_in + o);
+          if (PART_COLS > 32) prefetch_l2(p.s32_in + o + 32);
+        }
         prefetch_l2(p.c_in + o);
       }
       GLOM_CNT_WAIT(w0, mbar_wait(&tfull_bar[as], aphase));
@@ -421,7 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
         }
       } else {
         K2Chunk kc;
-        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0; kc.prow0 = row0 % p.n;
+        kc.l = t.z; kc.L = p.L; kc.d = p.d; kc.n = p.n; kc.row0 = row0; kc.prow0 = row0 % p.n; kc.s_bcast = p.s_bcast;
         kc.s32_in = p.s32_in; kc.c_in = p.c_in; kc.pos = p.pos;
         kc.s32_out = p.s32_out; kc.sb_out = p.sb_out; kc.sp_out = p.sp_out;
         float rowsq[8];
@@ -1218,7 +1221,7 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, int step_inde
     p.num_m = (rows + 255) / 256; p.num_n = d / g.bn2; p.z0 = 0; p.num_tiles = L * p.num_m * p.num_n;
     p.n_half = p.num_m * p.num_n;
     p.m128 = m128;
-    p.bias = b.b2; p.s32_in = b.s32_in; p.c_in = b.c; p.pos = b.pos;
+    p.bias = b.b2; p.s32_in = b.s32_in; p.s_bcast = b.s32_in_bcast; p.c_in = b.c; p.pos = b.pos;
     p.s32_out = b.s32_out; p.sb_out = b.sb_out; p.sp_out = b.sp_out; p.nsq_out = b.nsq_out; p.nparts = g.nparts;
     static int h_pf = -1;
     if (h_pf < 0) { const char* ev = getenv("GLOM_B200_K2_PREFETCH"); h_pf = ev ? atoi(ev) : 0; }
