@@ -60,6 +60,7 @@ struct GemmParams {
   int h_prefetch;  // K2: k-blocks of H prefetched into L2 ahead of the TMA loads (0 = off)
   int z_rev;        // K1: groups walked from G - 1 down to z0 (see step_bf16)
   int h_keep_z;     // K1: H blocks of groups <= h_keep_z are stored with the default L2 policy instead of streaming stores
+  int h_load_policy; // K2: L2 hint of the H loads (GLOM_B200_K2_HPOL, default 0 = evict-first on every load)
   int epi_prefetch; // K2: L2 prefetch of the epilogue's state / consensus lines at tile start (GLOM_B200_K2_EPI_PREFETCH, default on)
 };
 
@@ -290,7 +291,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0,   // K1: tokens Xb (rows
           if (MODE == 1) {
             const int blk = blk0 + kb + (kb >= kbg_n ? blk_skip : 0);
             // H streams through once per pair of column tiles: evict-first keeps it from displacing weights / state
-            tma_load_2d_2sm_sa_hint(sa, amap, bar, 0, blk * BM, pol_first);
+            // (h_load_policy, diagnostics: 1 = only the row block's last column tile marks it evict-first, 2 = no hint)
+            if (p.h_load_policy == 0 || (p.h_load_policy == 1 && t.n_blk == p.num_n - 1)) tma_load_2d_2sm_sa_hint(sa, amap, bar, 0, blk * BM, pol_first);
+            else tma_load_2d_2sm_sa(sa, amap, bar, 0, blk * BM);
           } else {
             tma_load_2d_2sm_sa(sa, amap, bar, a_col + kb * BK, a_row);
           }
@@ -1229,6 +1232,9 @@ int step_bf16(const Geometry& g, const Bf16Buffers& b, int* sched, int step_inde
     static int epi_pf = -1;
     if (epi_pf < 0) { const char* ev = getenv("GLOM_B200_K2_EPI_PREFETCH"); epi_pf = ev ? atoi(ev) : 1; }
     p.epi_prefetch = epi_pf;
+    static int k2_hpol = -1;
+    if (k2_hpol < 0) { const char* ev = getenv("GLOM_B200_K2_HPOL"); k2_hpol = ev ? atoi(ev) : 0; }
+    p.h_load_policy = k2_hpol;
     cudaError_t e;
     ProfScope scope(prof, PROF_GEMM2, st);
     if (g.bn2 == 256) e = launch_gemm<1, 256>(mh, mh, mh, mw2, p, num_sms, st);
