@@ -117,8 +117,6 @@ struct F32Buffers {
   const float* w1;  const float* w2;  const float* b1;  const float* b2;
 };
 cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, int* launches, Profiler* prof);
-// consensus on CUDA cores from the fp32 state, bf16 result (bf16 engine, n beyond the tensor-core kernel's capacity)
-cudaError_t attn_simt_bf16_out(const Geometry& g, const float* s32, __nv_bfloat16* c, cudaStream_t st, int* launches);
 cudaError_t launch_broadcast_init(const Geometry& g, const float* state_in, const float* init_levels, float* dst,
                                   cudaStream_t st, int* launches, Profiler* prof);
 

@@ -380,10 +380,6 @@ static cudaError_t launch_attn_simt(const Geometry& g, const float* s, OutT* c, 
   return cudaGetLastError();
 }
 
-cudaError_t attn_simt_bf16_out(const Geometry& g, const float* s32, __nv_bfloat16* c, cudaStream_t st, int* launches) {
-  return launch_attn_simt<__nv_bfloat16>(g, s32, c, st, launches);
-}
-
 cudaError_t step_f32(const Geometry& g, const F32Buffers& b, cudaStream_t st, int* launches, Profiler* prof) {
   // consensus
   {
