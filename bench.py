@@ -759,7 +759,7 @@ def main():
             clocks["in_kernel_ms_per_step"] = {k: v[1] / args.steps for k, v in kernel_clk.items()}
             clocks["block0_wait_fractions"] = {k: dict(zip(("mma_lane_waits_operands", "mma_lane_waits_accumulator",
                                                             "tma_lane_waits_slot", "epilogue_warp0_waits_accumulator",
-                                                            "epilogue_warp0_busy"), v[2]))
+                                                            "epilogue_warp0_busy", "consensus_output_work"), v[2]))
                                                for k, v in kernel_clk.items() if any(v[2])}
             clocks["device_sm_mhz_before"] = dev_mhz_min[0]
             clocks["device_sm_mhz_after"] = dev_mhz_min[1]

@@ -218,9 +218,9 @@ def kernel_clocks(reset=True):
     """{kind: (SM MHz inside the kernels, in-kernel ms, [wait fractions of block 0: MMA lane on operands, MMA lane on a free
     accumulator, TMA lane on a free slot, epilogue warp 0 on an accumulator, epilogue warp 0 busy])} since the last reset."""
     k = len(PROFILE_KINDS)
-    mhz, ms, wf = (ctypes.c_double * k)(), (ctypes.c_double * k)(), (ctypes.c_double * (5 * k))()
+    mhz, ms, wf = (ctypes.c_double * k)(), (ctypes.c_double * k)(), (ctypes.c_double * (6 * k))()
     check(load().glom_b200_kernel_clocks(mhz, ms, wf, k, int(bool(reset))))
-    return {PROFILE_KINDS[i]: (mhz[i], ms[i], [round(wf[5 * i + j], 4) for j in range(5)]) for i in range(k) if ms[i] > 0}
+    return {PROFILE_KINDS[i]: (mhz[i], ms[i], [round(wf[6 * i + j], 4) for j in range(6)]) for i in range(k) if ms[i] > 0}
 
 
 def mlp_schedule(cfg, batch, num_sms=148):

@@ -497,7 +497,7 @@ GLOM_B200_API int glom_b200_kernel_clocks(double* mhz_by_kind, double* ms_by_kin
     mhz_by_kind[i] = have ? 1e3 * (double)acc[i][0] / (double)acc[i][1] : 0.0;     // cycles per ns -> MHz
     ms_by_kind[i] = have ? 1e-6 * (double)acc[i][1] : 0.0;
     if (wait_frac)
-      for (int j = 0; j < 5; ++j) wait_frac[5 * i + j] = have && acc[i][0] ? (double)acc[i][2 + j] / (double)acc[i][0] : 0.0;
+      for (int j = 0; j < 6; ++j) wait_frac[6 * i + j] = have && acc[i][0] ? (double)acc[i][2 + j] / (double)acc[i][0] : 0.0;
   }
   return 0;
 }

@@ -532,6 +532,7 @@ struct AttnParams {
   float* ml_acc;                       // (rows, L, 2) fp32: stabiliser (log2 units), row sum
 };
 
+template <bool CNT>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64, 128, 1)
             const __grid_constant__ CUtensorMap map_k,    // box (64, khalf_rows, 1)
@@ -586,6 +587,13 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
   const bool clk_thread = blockIdx.x == 0 && warp == W_ALLOC && lane == 0;
   ClockSample clk_s{};
   if (clk_thread) clk_s = clock_sample_begin();
+  // diagnostic instantiation (GLOM_B200_WAIT_COUNTERS=1): block 0's wait / busy cycles per role, in g_kernel_clk[PROF_ATTN]:
+  // [2] MMA lane waiting for operands, [3] for a free TMEM buffer or for P, [4] TMA lane waiting for a free slot,
+  // [5] softmax warp 0 waiting for S / O in TMEM, [6] its softmax work, [7] its output work
+  const bool cnt_cta = CNT && blockIdx.x == 0;
+  unsigned long long* const cnt = g_kernel_clk[PROF_ATTN];
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;
+#define GLOM_CNT_WAIT(acc, stmt) do { if (cnt_cta) { const long long t_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t_); } else { stmt; } } while (0)
 
   if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer (both CTAs), warp-converged
@@ -603,7 +611,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         const int key0 = p.key0 + kb * 256 + (int)cta_rank * (w >> 1);        // this CTA's half of the key block
         for (int dc = 0; dc < p.d / BK; dc += cps) {
           const int nc = min(cps, p.d / BK - dc);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          GLOM_CNT_WAIT(w0, mbar_wait(&empty_bar[stage], phase ^ 1));
           if (elected) {
             const uint32_t s = stages0 + (uint32_t)stage * ATTN_SLOT_BYTES;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)nc * qk_tx);
@@ -622,7 +630,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         const int nbox = wdp >> 7;                                   // 64-column boxes in this CTA's half
         for (int vs = 0; vs < nvslot; ++vs) {
           const int nkc = min(2, p.nchunk - 2 * vs);               // 64-key chunks in this slot
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          GLOM_CNT_WAIT(w0, mbar_wait(&empty_bar[stage], phase ^ 1));
           if (elected) {
             const uint32_t s = stages0 + (uint32_t)stage * ATTN_SLOT_BYTES;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(nkc * nbox) * 8192u);
@@ -639,6 +647,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         }
       }
     }
+    if (cnt_cta && elected) atomicAdd(&cnt[4], w0);
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only), warp-converged
     if (leader) {
@@ -657,12 +666,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
           const int w = min(256, p.n_pad16 - kb * 256);
           const uint32_t idesc = umma_idesc_bf16(256, w, 0, 0);
           const uint32_t buf = job & 1;
-          mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
+          GLOM_CNT_WAIT(w1, mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1));
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + buf * 256u;
           for (int dc = 0; dc < p.d / BK; dc += cps) {
             const int nc = min(cps, p.d / BK - dc);
-            mbar_wait(&full_bar[stage], phase);
+            GLOM_CNT_WAIT(w0, mbar_wait(&full_bar[stage], phase));
             tc_fence_after_sync();
             if (elected) {
               const uint32_t s_lo = (stages0 + (uint32_t)stage * ATTN_SLOT_BYTES) >> 4;
@@ -682,18 +691,18 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
           __syncwarp();
         }
         // phase 2: O = P V   (A = P from smem, K-major; B = V slice, MN-major, 64 columns from each CTA)
-        mbar_wait_cluster(pready_bar, item_par);
+        GLOM_CNT_WAIT(w1, mbar_wait_cluster(pready_bar, item_par));
         tc_fence_after_sync();
         for (int sp = 0; sp < nsub; ++sp, ++job) {
           const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;
           const uint32_t idesc = umma_idesc_bf16(256, wdp, 0, 1);
           const uint32_t buf = job & 1;
-          mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1);
+          GLOM_CNT_WAIT(w1, mbar_wait(&aempty_bar[buf], ((job >> 1) & 1) ^ 1));
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + buf * 256u;
           for (int vs = 0; vs < nvslot; ++vs) {
             const int nkc = min(2, p.nchunk - 2 * vs);
-            mbar_wait(&full_bar[stage], phase);
+            GLOM_CNT_WAIT(w0, mbar_wait(&full_bar[stage], phase));
             tc_fence_after_sync();
             if (elected) {
               const uint32_t s_lo = (stages0 + (uint32_t)stage * ATTN_SLOT_BYTES) >> 4;
@@ -713,6 +722,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
           __syncwarp();
         }
       }
+      if (cnt_cta && elected) { atomicAdd(&cnt[2], w0); atomicAdd(&cnt[3], w1); }
     }
   } else if (warp < ATTN_SM_WARPS) {
     // ------------------------------------------------------------------ softmax + output warps (16 per CTA)
@@ -782,6 +792,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       const size_t img_row0 = (size_t)b * p.n;
       const float* rsc = rs + item_par * p.n_pad16;
       named_bar_sync(1, ATTN_SM_THREADS);      // this item's key scales are visible
+      const long long cnt_t0 = cnt_cta ? clock64() : 0;
+      const unsigned long long cnt_w0 = w0;
 
       const int qh = use_mask ? qi / p.mask_side : 0, qw = use_mask ? qi % p.mask_side : 0;
       const int diag = p.attend_self ? -1 : qi;
@@ -846,7 +858,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         const int w = min(256, p.n_pad16 - kb * 256);
         const int cbeg = (((w >> 4) * part) >> 2) << 4, cend = (((w >> 4) * (part + 1)) >> 2) << 4;   // 16-key blocks
         const uint32_t buf = job & 1;
-        mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+        GLOM_CNT_WAIT(w0, mbar_wait(&afull_bar[buf], (job >> 1) & 1));
         tc_fence_after_sync();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u;
         // S is read from TMEM 16 columns at a time; the loops stay rolled (one copy of the block body each)
@@ -931,6 +943,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
       fence_proxy_async_smem();                // this thread's P rows -> visible to the tensor core's reads
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(pready_remote);
+      const long long cnt_t1 = cnt_cta ? clock64() : 0;
+      const unsigned long long cnt_w1 = w0;
+      if (cnt_cta) w1 += (unsigned long long)(cnt_t1 - cnt_t0) - (cnt_w1 - cnt_w0);       // softmax work (waits excluded)
       // while P V runs: key scales of this cluster's next item (other parity; last read in the previous item)
       if (it + num_clusters < p.num_items) key_scales(it + num_clusters, item_par ^ 1);
       // key passes: this row's carried (stabiliser, row sum), read before the barrier below (part 0 rewrites it after it)
@@ -962,7 +977,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         const int wdp = (min(256, p.d - sp * 256) + 127) & ~127;
         const int cbeg = part * (wdp >> 2), cend = min(cbeg + (wdp >> 2), p.d - sp * 256);   // columns past d hold zeros
         const uint32_t buf = job & 1;
-        mbar_wait(&afull_bar[buf], (job >> 1) & 1);
+        GLOM_CNT_WAIT(w0, mbar_wait(&afull_bar[buf], (job >> 1) & 1));
         tc_fence_after_sync();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u;
         __nv_bfloat16* cdst = p.c_out + ((img_row0 + q0 + quad * 32) * p.L + l) * p.d + sp * 256;
@@ -1025,8 +1040,11 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q,    // (L*d, n, B) box (64
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(aempty_remote + 8u * buf);
       }
+      if (cnt_cta) w2 += (unsigned long long)(clock64() - cnt_t1) - (w0 - cnt_w1);          // key scales + output work
     }
+    if (cnt_cta && warp == 0 && lane == 0) { atomicAdd(&cnt[5], w0); atomicAdd(&cnt[6], w1); atomicAdd(&cnt[7], w2); }
   }
+#undef GLOM_CNT_WAIT
 
   tc_fence_before_sync();
   __syncthreads();
@@ -1146,7 +1164,10 @@ static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiled
     ap.num_stages = stages;
     const size_t smem = fixed + (size_t)stages * ATTN_SLOT_BYTES;
     static SmemOptIn optin;
-    if (cudaError_t e = optin.ensure(attn_kernel, smem)) {
+    static int count_waits = -1;
+    if (count_waits < 0) { const char* ev = getenv("GLOM_B200_WAIT_COUNTERS"); count_waits = (ev && ev[0] == '1') ? 1 : 0; }
+    static SmemOptIn optin_cnt;
+    if (cudaError_t e = count_waits ? optin_cnt.ensure(attn_kernel<true>, smem) : optin.ensure(attn_kernel<false>, smem)) {
       snprintf(err, errlen, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
       return -3;
     }
@@ -1163,7 +1184,8 @@ static int launch_attention(const Geometry& g, const Bf16Buffers& b, EncodeTiled
     aattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see pdl_wait() in the kernel
     aattr[1].val.programmaticStreamSerializationAllowed = 1;
     acfg.attrs = aattr; acfg.numAttrs = 2;
-    const cudaError_t e = cudaLaunchKernelEx(&acfg, attn_kernel, mq, mk, mv, ap);
+    const cudaError_t e = count_waits ? cudaLaunchKernelEx(&acfg, attn_kernel<true>, mq, mk, mv, ap)
+                                      : cudaLaunchKernelEx(&acfg, attn_kernel<false>, mq, mk, mv, ap);
     if (launches) ++*launches;
     if (e != cudaSuccess) { snprintf(err, errlen, "attn_kernel launch: %s", cudaGetErrorString(e)); return -3; }
   }

@@ -222,9 +222,11 @@ GLOM_B200_API int glom_b200_clock_probe(uint64_t* out_cycles_ns, int spin_us, vo
  * tcgen05 kernel brackets the kernel's working phase with (clock64, %globaltimer); the deltas accumulate per kernel kind
  * (indices as in glom_b200_profile_end: 0 consensus, 1 GEMM1+GELU, 2 GEMM2+combine, 4 tokeniser GEMM, 5 merged MLP kernel).
  * Writes MHz (cycles per microsecond of in-kernel time) and the in-kernel milliseconds per kind since the last reset;
- * kinds without samples report 0.  wait_frac (may be NULL, else 5 doubles per kind): fractions of block 0's in-kernel
- * cycles that {the MMA lane waited for operands, the MMA lane waited for a free accumulator stage, the TMA lane waited
- * for a free ring slot, epilogue warp 0 waited for an accumulator, epilogue warp 0 was busy} (GEMM kernels only).
+ * kinds without samples report 0.  wait_frac (may be NULL, else 6 doubles per kind): fractions of block 0's in-kernel
+ * cycles that {the MMA lane waited for operands, the MMA lane waited for a free accumulator stage (consensus: TMEM buffer
+ * or P), the TMA lane waited for a free ring slot, epilogue / softmax warp 0 waited for an accumulator, that warp was
+ * busy (consensus: softmax work), consensus only: its output work}; filled by the diagnostic instantiations only
+ * (environment variable GLOM_B200_WAIT_COUNTERS=1).
  * Synchronises the device; `reset` != 0 clears the accumulators. */
 GLOM_B200_API int glom_b200_kernel_clocks(double* mhz_by_kind, double* ms_by_kind, double* wait_frac, int kinds, int reset);
 
