@@ -79,7 +79,7 @@ constexpr uint32_t STAGE_BYTES = 32768;
 constexpr int STAGES = 5;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 32 * (EPI_WARPS + 4);
-enum { F_T = 1, F_A = 2, F_S = 4, F_G = 8, F_R = 16, F_H = 32, F_B = 64, F_D = 128, F_X = 256, F_W = 512, F_L = 1024 };
+enum { F_T = 1, F_A = 2, F_S = 4, F_G = 8, F_R = 16, F_H = 32, F_B = 64, F_D = 128, F_X = 256, F_W = 512, F_L = 1024, F_P = 2048 };
 
 template <int FLAGS, int DIET>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -218,6 +218,51 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     out[blockIdx.x].kblocks = (unsigned long long)tiles * nkb;
     out[blockIdx.x].wait_full = wf;
     out[blockIdx.x].wait_acc = wa;
+  } else if ((FLAGS & F_P) && warp < EPI_WARPS) {
+    // T+A+S+G with the TMEM read-out software-pipelined in 16-column quarters: the next quarter's tcgen05.ld is in flight
+    // while the current one goes through the GELU
+    const int quad = warp & 3, part = warp >> 2;
+    uint8_t* patch = patches + (size_t)warp * 4096;
+    int as = 0; uint32_t aphase = 0;
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + part * 64);
+      const size_t blk = ((size_t)(cluster_id + (size_t)t * num_clusters) * 2 + rank) * 4 + part;
+      uint8_t* hrow = hbuf + (blk * 16384) % hbytes + (size_t)quad * 32 * 128;
+      uint32_t qa[16], qb[16], pk[16];
+      tmem_ld16(t_addr, qa);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tmem_ld_wait();
+        if (q < 3) { if (q & 1) tmem_ld16(t_addr + 16 * (q + 1), qa); else tmem_ld16(t_addr + 16 * (q + 1), qb); }
+        const float* b = bias_s + part * 64 + q * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t x0 = (q & 1) ? qb[2 * i] : qa[2 * i], x1 = (q & 1) ? qb[2 * i + 1] : qa[2 * i + 1];
+          pk[8 * (q & 1) + i] = gelu_pair_bf16(__uint_as_float(x0), __uint_as_float(x1), b[2 * i], b[2 * i + 1]);
+        }
+        if (q & 1) {
+          const int c0 = (q >> 1) * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(patch + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          __syncwarp();
+          const int c = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2);
+            const uint4 val = *reinterpret_cast<const uint4*>(patch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+            __stcs(reinterpret_cast<uint4*>(hrow + (size_t)r * 128 + c0 * 2 + c * 16), val);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
   } else if ((FLAGS & F_D) && warp < EPI_WARPS) {
     // T+A+S+G with the warps split into two groups half a period apart: "late" warps (odd column parts) store a chunk's
     // packed results one chunk later, right after issuing the next TMEM load -- while the "early" warps are in their
@@ -469,9 +514,7 @@ int main(int argc, char** argv) {
   printf("GEMM1-shaped tiles (256 x 256 per CTA pair) with the epilogue added back piece by piece, %d SMs\n", sms);
   const int nkb = argc > 1 ? atoi(argv[1]) : 8, tiles = argc > 2 ? atoi(argv[2]) : 400;
 #define RUN(F, D, NAME) run<F, D>(NAME, ma, mb, sms, nkb, tiles, a_rows_total, dres, hbuf, hbytes, bias)
-  RUN(F_T | F_S | F_G, 1, "T+S+G");
-  RUN(F_T | F_L, 1, "T+L (full-line stores)");
   RUN(F_T | F_A | F_S | F_G, 1, "T+A+S+G");
-  RUN(F_T | F_A | F_L, 1, "T+A+L");
+  RUN(F_P, 1, "T+A+S+G, TMEM read-out pipelined in quarters");
   return 0;
 }
