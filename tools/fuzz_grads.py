@@ -11,7 +11,8 @@ for it in range(N):
     dim = int(rng.choice([256, 512]))
     L = int(rng.integers(2, 5))
     p = 2
-    side = int(rng.choice([2, 3, 8, 10, 11, 16, 18, 20]))
+    side = int(rng.choice([2, 3, 8, 10, 11, 16, 18, 20, 26, 28]))     # 26, 28: n = 676 / 784 > 576 columns
+    if side >= 26: dim = 256
     B = int(rng.integers(1, 4)); T = int(rng.integers(1, 3))
     kw = {}
     if rng.random() < 0.3: kw["consensus_self"] = True
